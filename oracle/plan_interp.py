@@ -1,0 +1,138 @@
+"""ORACLE-side tool (test infrastructure): executes a lowered plan
+(peppa_pig_face_landmark_b200.plan.Plan) with PyTorch CPU ops so that the
+lowering — fusion patterns, concat/shuffle views, decode tails — can be checked
+against oracle.onnx_exec without a GPU.  Mirrors the semantics csrc/ implements."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from peppa_pig_face_landmark_b200 import plan as P
+
+
+def _act(x, a):
+    if a == P.ACT_NONE:
+        return x
+    if a == P.ACT_RELU:
+        return torch.relu(x)
+    if a == P.ACT_SILU:
+        return x * torch.sigmoid(x)
+    if a == P.ACT_SIGMOID:
+        return torch.sigmoid(x)
+    hs = torch.clamp(x * np.float32(1.0 / 6.0) + 0.5, 0.0, 1.0)
+    return x * hs if a == P.ACT_HSWISH else hs
+
+
+class PlanInterp:
+    def __init__(self, plan):
+        self.plan = plan
+
+    def run(self, x_nhwc, dump=None):
+        """x: (N,H,W,3) uint8 (or float32 already /255 when the plan was lowered with input_u8=False)."""
+        pl = self.plan
+        N = x_nhwc.shape[0]
+        bufs = [torch.zeros(N, b.H, b.W, b.C, dtype=torch.float32) for b in pl.bufs]
+        xin = torch.from_numpy(np.ascontiguousarray(x_nhwc))
+        if xin.dtype == torch.uint8:
+            xin = xin.to(torch.float32) / np.float32(255.0)
+        bufs[pl.input.buf.idx] = xin
+
+        def rd(v):
+            return bufs[v.buf.idx][..., v.c_off: v.c_off + v.C * v.c_stride: v.c_stride]
+
+        def wr(v, val):
+            bufs[v.buf.idx][..., v.c_off: v.c_off + v.C * v.c_stride: v.c_stride] = val
+
+        for op in pl.ops:
+            t = op.type
+            if t == P.OP_CONV:
+                x = rd(op.ins[0])
+                if op.ins[2] is not None:
+                    x = x * rd(op.ins[2])
+                w = torch.from_numpy(op.w).permute(0, 3, 1, 2).contiguous()
+                y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b) if op.b is not None else None,
+                             stride=op.s, padding=tuple(op.p), dilation=op.d)
+                y = _act(y, op.act).permute(0, 2, 3, 1)
+                if op.ins[1] is not None:
+                    y = y + rd(op.ins[1])
+                wr(op.outs[0], y)
+            elif t == P.OP_DWCONV:
+                x = rd(op.ins[0])
+                C = x.shape[-1]
+                w = torch.from_numpy(op.w).T.reshape(C, 1, op.k[0], op.k[1]).contiguous()
+                y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b), stride=op.s, padding=tuple(op.p),
+                             dilation=op.d, groups=C)
+                wr(op.outs[0], _act(y, op.act).permute(0, 2, 3, 1))
+            elif t == P.OP_MAXPOOL2:
+                x = rd(op.ins[0]).permute(0, 3, 1, 2)
+                wr(op.outs[0], F.max_pool2d(x, 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1))
+            elif t == P.OP_RESIZE_NEAREST:
+                x = rd(op.ins[0])
+                o = op.outs[0]
+                ys = (torch.arange(o.H) * x.shape[1]) // o.H
+                xs = (torch.arange(o.W) * x.shape[2]) // o.W
+                wr(o, x[:, ys][:, :, xs])
+            elif t == P.OP_UPSAMPLE_BILINEAR2X:
+                x = rd(op.ins[0]).permute(0, 3, 1, 2)
+                y = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+                wr(op.outs[0], y.permute(0, 2, 3, 1))
+            elif t == P.OP_COPY:
+                wr(op.outs[0], rd(op.ins[0]).clone())
+            elif t == P.OP_GAP:
+                wr(op.outs[0], rd(op.ins[0]).mean(dim=(1, 2), keepdim=True))
+            elif t == P.OP_AFFINE_ACT:
+                y = rd(op.ins[0]) * torch.from_numpy(op.w) + torch.from_numpy(op.b)
+                wr(op.outs[0], _act(y, op.act))
+            elif t == P.OP_SCSE:
+                x = rd(op.ins[0])
+                wr(op.outs[0], x * rd(op.ins[1]) + x * rd(op.ins[2]))
+            elif t == P.OP_DET_DECODE:
+                wr(op.outs[0], self._det_decode(op, [rd(v) for v in op.ins], N))
+            elif t == P.OP_HM_DECODE:
+                xy, sc = self._hm_decode(rd(op.ins[0]), op.ints[0])
+                wr(op.outs[0], xy.reshape(N, 1, 1, -1))
+                wr(op.outs[1], sc.reshape(N, 1, 1, -1))
+            else:
+                raise NotImplementedError(t)
+            if dump is not None:
+                dump.append((op, [rd(o).clone() for o in op.outs]))
+        return [rd(v).reshape(N, -1).numpy() if v.buf.W == 1 and v.buf.H == 1
+                else rd(v).reshape(N, v.buf.H, v.C).numpy() for v in pl.outputs]
+
+    @staticmethod
+    def _det_decode(op, heads, N):
+        c = op.w
+        rows = []
+        for si, h in enumerate(heads):
+            stride = c[si * 7]
+            anchors = torch.from_numpy(c[si * 7 + 1: si * 7 + 7].reshape(3, 2).copy())
+            H, W = h.shape[1], h.shape[2]
+            t = h.reshape(N, H, W, 3, 16).permute(0, 3, 1, 2, 4)          # N,3,H,W,16
+            gy, gx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32),
+                                    indexing="ij")
+            grid = torch.stack([gx, gy], -1)[None, None]
+            an = anchors[None, :, None, None, :]
+            sg = torch.sigmoid(t)
+            xy = (sg[..., 0:2] * 2.0 - 0.5 + grid) * stride
+            wh = (sg[..., 2:4] * 2.0) ** 2 * an
+            parts = [xy, wh, sg[..., 4:5]]
+            for k in range(5):
+                parts.append(t[..., 5 + 2 * k: 7 + 2 * k] * an + grid * stride)
+            parts.append(sg[..., 15:16])
+            rows.append(torch.cat(parts, -1).reshape(N, -1, 16))
+        return torch.cat(rows, 1).reshape(N, -1, 1, 16)
+
+    @staticmethod
+    def _hm_decode(hm, npts):
+        N, H, W, C = hm.shape
+        flat = hm.reshape(N, H * W, C)
+        heat = flat[..., :npts]
+        m = heat.max(dim=1, keepdim=True).values
+        ar = torch.arange(H * W).reshape(1, -1, 1)
+        idx = torch.where(heat == m, ar, torch.full_like(ar, H * W)).min(dim=1).values     # N,npts
+        g = idx[:, None, :]
+        sc = torch.gather(heat, 1, g)[:, 0]
+        ox = torch.gather(flat[..., npts:2 * npts], 1, g)[:, 0]
+        oy = torch.gather(flat[..., 2 * npts:3 * npts], 1, g)[:, 0]
+        x = ((idx % W).to(torch.float32) + ox) / np.float32(W)
+        y = ((idx // W).to(torch.float32) + oy) / np.float32(W)
+        return torch.stack([x, y], -1), sc

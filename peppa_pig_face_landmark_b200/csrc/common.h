@@ -1,0 +1,114 @@
+// Shared declarations for libskps_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace skps {
+
+// ---- op codes / activations: keep in sync with peppa_pig_face_landmark_b200/plan.py ----
+enum OpType {
+    OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
+    OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11
+};
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
+enum { DT_F32 = 0, DT_U8 = 1 };
+enum { FLAG_IN_U8 = 1 };
+enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
+
+struct View {            // 6 words
+    int32_t buf, c_off, c_stride, C, H, W;
+};
+struct OpDesc {          // 64 words
+    int32_t type, act;
+    View in[3];
+    View out[2];
+    int32_t kh, kw, sh, sw, ph, pw, dh, dw;
+    int32_t w_off, b_off, flags;
+    int32_t i[4];
+    float f[8];
+    int32_t pad[64 - (2 + 30 + 8 + 3 + 4 + 8)];
+};
+static_assert(sizeof(OpDesc) == 64 * 4, "OpDesc must be 64 words");
+
+struct BufDesc { int32_t C, H, W, dtype; };
+
+// A resolved tensor view on device memory (NHWC, batch outermost).
+struct TView {
+    void* base;        // buffer base (sample 0)
+    int ld;            // channels of the underlying buffer (row pitch in elements per pixel)
+    int c_off, c_stride, C, H, W;
+    long long sample;  // elements per sample = H*W*ld
+};
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SKPS_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            skps::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define SKPS_CHECK(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            skps::set_error(__VA_ARGS__);     \
+            return 1;                         \
+        }                                     \
+    } while (0)
+
+// ---- activation (device) -------------------------------------------------------------------
+// HardSigmoid follows ONNX: max(0, min(1, alpha*x + beta)) with alpha = float32(1/6), beta = 0.5
+// (kps_student.onnx node 2 etc.); alpha*x+beta is evaluated as mul then add (no FMA) to match a
+// CPU execution provider's two-step evaluation as closely as possible.
+__device__ __forceinline__ float hsigmoid_f(float x) {
+    float t = __fadd_rn(__fmul_rn(x, 0.1666666716337204f), 0.5f);
+    return fminf(fmaxf(t, 0.f), 1.f);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    switch (act) {
+        case ACT_RELU: return fmaxf(v, 0.f);
+        case ACT_HSWISH: return v * hsigmoid_f(v);
+        case ACT_SILU: return v * sigmoid_f(v);
+        case ACT_SIGMOID: return sigmoid_f(v);
+        case ACT_HSIGMOID: return hsigmoid_f(v);
+        default: return v;
+    }
+}
+
+// ---- kernel launchers (defined in the .cu files) ---------------------------------------------
+struct ConvArgs {
+    TView in, out, res, gate;     // res.base / gate.base may be null
+    const float* w;               // [Cout][kh*kw][Cin]
+    const float* bias;            // may be null
+    int kh, kw, sh, sw, ph, pw, dh, dw, act, in_u8, batch;
+};
+int launch_conv(const ConvArgs& a, cudaStream_t s);
+
+struct DwArgs {
+    TView in, out;
+    const float* w;               // [kh*kw][C]
+    const float* bias;
+    int kh, kw, sh, sw, ph, pw, dh, dw, act, batch;
+};
+int launch_dwconv(const DwArgs& a, cudaStream_t s);
+
+int launch_maxpool2(const TView& in, const TView& out, int batch, cudaStream_t s);
+int launch_resize_nearest(const TView& in, const TView& out, int batch, cudaStream_t s);
+int launch_bilinear2x(const TView& in, const TView& out, int batch, cudaStream_t s);
+int launch_copy(const TView& in, const TView& out, int batch, cudaStream_t s);
+int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s);
+int launch_affine_act(const TView& in, const TView& out, const float* sc, const float* sh, int act, int batch,
+                      cudaStream_t s);
+int launch_scse(const TView& x, const TView& cse, const TView& sse, const TView& out, int batch, cudaStream_t s);
+int launch_det_decode(const TView* heads, const float* consts, const TView& out, int rows, int batch, cudaStream_t s);
+int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s);
+
+}  // namespace skps

@@ -1,0 +1,308 @@
+// skps_engine: runs one lowered network plan (peppa_pig_face_landmark_b200/plan.py) on one GPU.
+// Stands where onnxruntime.InferenceSession stands in the reference
+// (Skps/core/api/onnx_model_base.py:14,23).  Owns the packed weights and all activation buffers
+// (sized for max_batch at creation: no allocation on the forward path); the op sequence for a
+// given batch size is captured once into a CUDA graph and replayed.
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <vector>
+
+#include "../../include/skps_b200.h"
+#include "common.h"
+
+namespace skps {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+}  // namespace skps
+
+using namespace skps;
+
+struct skps_engine {
+    int device = 0, max_batch = 0;
+    std::vector<BufDesc> bufs;
+    std::vector<void*> dbuf;              // device buffers, max_batch samples each
+    std::vector<OpDesc> ops;
+    float* d_weights = nullptr;
+    std::vector<float> h_weights;
+    size_t n_weights = 0;
+    int input_buf = -1;
+    std::vector<int> output_bufs;
+    float* d_stage_f32 = nullptr;         // staging for NCHW float32 host input
+    float* d_in_f32 = nullptr;            // NHWC float32 copy of that input (f32_mode)
+    bool f32_mode = false;                // first conv reads d_in_f32 instead of the uint8 input buffer
+    std::map<int, cudaGraphExec_t> graphs;   // batch -> captured forward
+    int launches = 0;
+    bool use_graph = true;
+};
+
+static size_t buf_elems(const BufDesc& b) { return (size_t)b.C * b.H * b.W; }
+static size_t buf_bytes(const BufDesc& b) { return buf_elems(b) * (b.dtype == DT_U8 ? 1 : 4); }
+
+static TView resolve(const skps_engine* e, const View& v) {
+    TView t;
+    memset(&t, 0, sizeof(t));
+    if (v.buf < 0) return t;
+    const BufDesc& b = e->bufs[v.buf];
+    t.base = (v.buf == e->input_buf && e->f32_mode) ? (void*)e->d_in_f32 : e->dbuf[v.buf];
+    t.ld = b.C;
+    t.c_off = v.c_off; t.c_stride = v.c_stride; t.C = v.C; t.H = b.H; t.W = b.W;
+    t.sample = (long long)b.C * b.H * b.W;
+    return t;
+}
+
+static int run_ops(skps_engine* e, int batch, cudaStream_t s) {
+    for (size_t i = 0; i < e->ops.size(); ++i) {
+        const OpDesc& op = e->ops[i];
+        TView in0 = resolve(e, op.in[0]), in1 = resolve(e, op.in[1]), in2 = resolve(e, op.in[2]);
+        TView out0 = resolve(e, op.out[0]), out1 = resolve(e, op.out[1]);
+        const float* w = op.w_off >= 0 ? e->d_weights + op.w_off : nullptr;
+        const float* b = op.b_off >= 0 ? e->d_weights + op.b_off : nullptr;
+        int rc = 0;
+        switch (op.type) {
+            case OP_CONV: {
+                ConvArgs a;
+                a.in = in0; a.res = in1; a.gate = in2; a.out = out0; a.w = w; a.bias = b;
+                a.kh = op.kh; a.kw = op.kw; a.sh = op.sh; a.sw = op.sw; a.ph = op.ph; a.pw = op.pw;
+                a.dh = op.dh; a.dw = op.dw; a.act = op.act; a.in_u8 = ((op.flags & FLAG_IN_U8) && !e->f32_mode) ? 1 : 0;
+                a.batch = batch;
+                rc = launch_conv(a, s);
+                break;
+            }
+            case OP_DWCONV: {
+                DwArgs a;
+                a.in = in0; a.out = out0; a.w = w; a.bias = b;
+                a.kh = op.kh; a.kw = op.kw; a.sh = op.sh; a.sw = op.sw; a.ph = op.ph; a.pw = op.pw;
+                a.dh = op.dh; a.dw = op.dw; a.act = op.act; a.batch = batch;
+                rc = launch_dwconv(a, s);
+                break;
+            }
+            case OP_MAXPOOL2: rc = launch_maxpool2(in0, out0, batch, s); break;
+            case OP_RESIZE_NEAREST: rc = launch_resize_nearest(in0, out0, batch, s); break;
+            case OP_UPSAMPLE_BILINEAR2X: rc = launch_bilinear2x(in0, out0, batch, s); break;
+            case OP_COPY: rc = launch_copy(in0, out0, batch, s); break;
+            case OP_GAP: rc = launch_gap(in0, out0, batch, s); break;
+            case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
+            case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
+            case OP_DET_DECODE: {
+                TView heads[3] = {in0, in1, in2};
+                rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);
+                break;
+            }
+            case OP_HM_DECODE: rc = launch_hm_decode(in0, out0, out1, op.i[0], batch, s); break;
+            default: set_error("engine: unknown op type %d (op %zu)", op.type, i); return 1;
+        }
+        if (rc) {
+            char tmp[900];
+            snprintf(tmp, sizeof(tmp), "%s", get_error());
+            set_error("op %zu (type %d): %s", i, op.type, tmp);
+            return 1;
+        }
+    }
+    return 0;
+}
+
+extern "C" SKPS_API const char* skps_last_error(void) { return get_error(); }
+extern "C" SKPS_API int skps_version(void) { return 1; }
+
+extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words, const float* weights, size_t n_floats,
+                                  int max_batch, int device, skps_engine** out) {
+    SKPS_CHECK(words && weights && out && n_words >= 8 && max_batch > 0, "engine_create: bad arguments");
+    SKPS_CHECK(words[0] == PLAN_MAGIC && words[1] == 1, "engine_create: bad plan header");
+    int n_bufs = words[2], n_ops = words[3];
+    SKPS_CHECK(n_words == (size_t)8 + 4 * (size_t)n_bufs + OP_WORDS * (size_t)n_ops, "engine_create: plan size mismatch");
+    SKPS_CUDA(cudaSetDevice(device));
+    skps_engine* e = new skps_engine();
+    e->device = device;
+    e->max_batch = max_batch;
+    e->input_buf = words[4];
+    for (int i = 0; i < words[5]; ++i) e->output_bufs.push_back(words[6 + i]);
+    const int32_t* p = words + 8;
+    for (int i = 0; i < n_bufs; ++i, p += 4) e->bufs.push_back(BufDesc{p[0], p[1], p[2], p[3]});
+    e->ops.resize(n_ops);
+    memcpy(e->ops.data(), p, sizeof(OpDesc) * n_ops);
+    e->h_weights.assign(weights, weights + n_floats);
+    e->n_weights = n_floats;
+    e->launches = n_ops;
+    auto fail = [&](const char* what) {
+        char tmp[900];
+        snprintf(tmp, sizeof(tmp), "%s", get_error());
+        set_error("engine_create: %s: %s", what, tmp);
+        skps_engine_destroy(e);
+        return 1;
+    };
+    if (cudaMalloc(&e->d_weights, n_floats * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc weights"); return fail("alloc"); }
+    if (cudaMemcpy(e->d_weights, weights, n_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("cudaMemcpy weights"); return fail("copy");
+    }
+    e->dbuf.assign(n_bufs, nullptr);
+    for (int i = 0; i < n_bufs; ++i) {
+        size_t bytes = buf_bytes(e->bufs[i]) * (size_t)max_batch;
+        if (cudaMalloc(&e->dbuf[i], bytes ? bytes : 16) != cudaSuccess) {
+            set_error("cudaMalloc buffer %d (%zu bytes)", i, bytes);
+            return fail("alloc");
+        }
+        cudaMemset(e->dbuf[i], 0, bytes);
+    }
+    const BufDesc& ib = e->bufs[e->input_buf];
+    if (cudaMalloc(&e->d_stage_f32, buf_elems(ib) * sizeof(float) * (size_t)max_batch) != cudaSuccess ||
+        cudaMalloc(&e->d_in_f32, buf_elems(ib) * sizeof(float) * (size_t)max_batch) != cudaSuccess) {
+        set_error("cudaMalloc staging");
+        return fail("alloc");
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" SKPS_API void skps_engine_destroy(skps_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    for (void* p : e->dbuf) if (p) cudaFree(p);
+    if (e->d_weights) cudaFree(e->d_weights);
+    if (e->d_stage_f32) cudaFree(e->d_stage_f32);
+    if (e->d_in_f32) cudaFree(e->d_in_f32);
+    delete e;
+}
+
+extern "C" SKPS_API int skps_engine_input_dims(const skps_engine* e, int* h, int* w, int* c) {
+    SKPS_CHECK(e, "null engine");
+    const BufDesc& b = e->bufs[e->input_buf];
+    if (h) *h = b.H;
+    if (w) *w = b.W;
+    if (c) *c = b.C;
+    return 0;
+}
+extern "C" SKPS_API int skps_engine_num_outputs(const skps_engine* e) { return e ? (int)e->output_bufs.size() : 0; }
+extern "C" SKPS_API int skps_engine_output_elems(const skps_engine* e, int idx) {
+    if (!e || idx < 0 || idx >= (int)e->output_bufs.size()) return 0;
+    return (int)buf_elems(e->bufs[e->output_bufs[idx]]);
+}
+extern "C" SKPS_API void* skps_engine_input_ptr(skps_engine* e) { return e ? e->dbuf[e->input_buf] : nullptr; }
+extern "C" SKPS_API float* skps_engine_output_ptr(skps_engine* e, int idx) {
+    if (!e || idx < 0 || idx >= (int)e->output_bufs.size()) return nullptr;
+    return (float*)e->dbuf[e->output_bufs[idx]];
+}
+extern "C" SKPS_API int skps_engine_num_buffers(const skps_engine* e) { return e ? (int)e->bufs.size() : 0; }
+extern "C" SKPS_API int skps_engine_buffer_dims(const skps_engine* e, int buf, int* h, int* w, int* c, int* dtype) {
+    SKPS_CHECK(e && buf >= 0 && buf < (int)e->bufs.size(), "buffer_dims: bad index");
+    const BufDesc& b = e->bufs[buf];
+    if (h) *h = b.H;
+    if (w) *w = b.W;
+    if (c) *c = b.C;
+    if (dtype) *dtype = b.dtype;
+    return 0;
+}
+extern "C" SKPS_API int skps_engine_read_buffer(skps_engine* e, int buf, int batch, void* dst) {
+    SKPS_CHECK(e && buf >= 0 && buf < (int)e->bufs.size() && batch <= e->max_batch, "read_buffer: bad arguments");
+    SKPS_CUDA(cudaSetDevice(e->device));
+    SKPS_CUDA(cudaDeviceSynchronize());
+    SKPS_CUDA(cudaMemcpy(dst, e->dbuf[buf], buf_bytes(e->bufs[buf]) * batch, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" SKPS_API int skps_engine_launches_per_forward(const skps_engine* e) { return e ? e->launches : 0; }
+
+// Enqueue the op sequence (through a cached CUDA graph when possible).
+static int enqueue(skps_engine* e, int batch, cudaStream_t s) {
+    if (!e->use_graph || s == nullptr) return run_ops(e, batch, s);   // the legacy default stream cannot be captured
+    const int key = batch * 2 + (e->f32_mode ? 1 : 0);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        cudaStreamCaptureStatus st;
+        SKPS_CUDA(cudaStreamIsCapturing(s, &st));
+        if (st != cudaStreamCaptureStatusNone) return run_ops(e, batch, s);   // already inside a capture
+        cudaGraph_t g = nullptr;
+        SKPS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = run_ops(e, batch, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        SKPS_CUDA(ce);
+        cudaGraphExec_t ge = nullptr;
+        SKPS_CUDA(cudaGraphInstantiate(&ge, g, 0));
+        cudaGraphDestroy(g);
+        it = e->graphs.emplace(key, ge).first;
+    }
+    SKPS_CUDA(cudaGraphLaunch(it->second, s));
+    return 0;
+}
+
+static int copy_outputs(skps_engine* e, int batch, float* const* outputs, cudaMemcpyKind kind, cudaStream_t s) {
+    if (!outputs) return 0;
+    for (size_t i = 0; i < e->output_bufs.size(); ++i) {
+        if (!outputs[i]) continue;
+        const BufDesc& b = e->bufs[e->output_bufs[i]];
+        SKPS_CUDA(cudaMemcpyAsync(outputs[i], e->dbuf[e->output_bufs[i]], buf_bytes(b) * batch, kind, s));
+    }
+    return 0;
+}
+
+extern "C" SKPS_API int skps_engine_forward(skps_engine* e, const uint8_t* input, int batch, float* const* outputs,
+                                   void* stream) {
+    SKPS_CHECK(e && input, "forward: null argument");
+    SKPS_CHECK(batch > 0 && batch <= e->max_batch, "forward: batch %d outside 1..%d", batch, e->max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    SKPS_CUDA(cudaSetDevice(e->device));
+    const BufDesc& ib = e->bufs[e->input_buf];
+    SKPS_CHECK(ib.dtype == DT_U8, "forward: engine input is not uint8");
+    if ((const void*)input != e->dbuf[e->input_buf])
+        SKPS_CUDA(cudaMemcpyAsync(e->dbuf[e->input_buf], input, buf_bytes(ib) * batch, cudaMemcpyDeviceToDevice, s));
+    if (enqueue(e, batch, s)) return 1;
+    return copy_outputs(e, batch, outputs, cudaMemcpyDeviceToDevice, s);
+}
+
+// float32 NCHW -> float32 NHWC (ONNXEngine.__call__ feeds NCHW, onnx_model_base.py:17).
+__global__ void nchw_to_nhwc_f32(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W,
+                                 long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long long pix = i / C;
+    int x = (int)(pix % W);
+    long long t = pix / W;
+    int y = (int)(t % H);
+    long long n = t / H;
+    dst[i] = src[((n * C + c) * H + y) * W + x];
+}
+
+extern "C" SKPS_API int skps_engine_forward_host_u8(skps_engine* e, const uint8_t* input, int batch, float* const* outputs,
+                                           void* stream) {
+    SKPS_CHECK(e && input, "forward_host_u8: null argument");
+    SKPS_CHECK(batch > 0 && batch <= e->max_batch, "forward: batch %d outside 1..%d", batch, e->max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    SKPS_CUDA(cudaSetDevice(e->device));
+    const BufDesc& ib = e->bufs[e->input_buf];
+    SKPS_CUDA(cudaMemcpyAsync(e->dbuf[e->input_buf], input, buf_bytes(ib) * batch, cudaMemcpyHostToDevice, s));
+    if (enqueue(e, batch, s)) return 1;
+    if (copy_outputs(e, batch, outputs, cudaMemcpyDeviceToHost, s)) return 1;
+    SKPS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" SKPS_API int skps_engine_forward_host_f32(skps_engine* e, const float* input, int batch, float* const* outputs,
+                                            void* stream) {
+    SKPS_CHECK(e && input, "forward_host_f32: null argument");
+    SKPS_CHECK(batch > 0 && batch <= e->max_batch, "forward: batch %d outside 1..%d", batch, e->max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    SKPS_CUDA(cudaSetDevice(e->device));
+    const BufDesc& ib = e->bufs[e->input_buf];
+    long long total = (long long)buf_elems(ib) * batch;
+    SKPS_CUDA(cudaMemcpyAsync(e->d_stage_f32, input, total * sizeof(float), cudaMemcpyHostToDevice, s));
+    nchw_to_nhwc_f32<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(e->d_stage_f32, e->d_in_f32, ib.C, ib.H, ib.W, total);
+    SKPS_CUDA(cudaGetLastError());
+    e->f32_mode = true;
+    int rc = enqueue(e, batch, s);
+    e->f32_mode = false;
+    if (rc) return 1;
+    if (copy_outputs(e, batch, outputs, cudaMemcpyDeviceToHost, s)) return 1;
+    SKPS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}

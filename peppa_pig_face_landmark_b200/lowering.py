@@ -1,0 +1,550 @@
+"""ONNX graph -> fused execution plan (plan.Plan).
+
+Replaces what onnxruntime's graph optimiser + kernels do for the reference
+(/root/reference/Skps/core/api/onnx_model_base.py:14): the shipped graphs
+(yolov5n-0.5.onnx, kps_student.onnx) are pattern-matched into the op set in
+plan.py.  Patterns handled:
+
+  Conv [+Sigmoid,Mul | +HardSigmoid,Mul | +Relu | +Sigmoid | +HardSigmoid] [+Add]   -> OP_CONV / OP_DWCONV
+  ReduceMean(2,3) / GlobalAveragePool                                               -> OP_GAP
+  Mul(x, gate[N,C,1,1]) feeding a Conv (squeeze-excite)                             -> conv input scale
+  Mul(x,cSE) + Mul(x,sSE) -> Add (scSE attention)                                   -> OP_SCSE
+  Concat(axis=1), Slice(axis=1), Reshape-Transpose-Reshape channel shuffle          -> views (no data movement)
+  Resize nearest / linear x2, MaxPool 2x2 ceil, BatchNormalization [+Relu]          -> small ops
+  yolov5-face Detect tail (face_detector graph nodes 502-820)                       -> OP_DET_DECODE
+  heat-map arg-max tail (kps graph nodes 201-410; model.py:511-554)                 -> OP_HM_DECODE
+"""
+import numpy as np
+
+from . import plan as P
+from .onnx_loader import load_onnx
+
+
+class LoweringError(RuntimeError):
+    pass
+
+
+def _fold(node, vals):
+    """Constant-fold the small shape-arithmetic ops the exporters leave behind."""
+    op, a = node.op, node.attrs
+    x = [vals[i] if i != "" else None for i in node.inputs]
+    if op == "Add":
+        return x[0] + x[1]
+    if op == "Sub":
+        return x[0] - x[1]
+    if op == "Mul":
+        return x[0] * x[1]
+    if op == "Div":
+        if np.issubdtype(np.asarray(x[0]).dtype, np.integer):
+            return np.trunc(np.asarray(x[0]) / np.asarray(x[1])).astype(np.int64)
+        return x[0] / x[1]
+    if op == "Gather":
+        return np.take(x[0], x[1], axis=a.get("axis", 0))
+    if op == "Concat":
+        return np.concatenate([np.atleast_1d(v) for v in x], axis=a["axis"])
+    if op == "Unsqueeze":
+        out = np.asarray(x[0])
+        for ax in sorted(a["axes"]):
+            out = np.expand_dims(out, ax)
+        return out
+    if op == "Squeeze":
+        return np.squeeze(x[0], axis=tuple(a["axes"]))
+    if op == "Cast":
+        return np.asarray(x[0]).astype({1: np.float32, 7: np.int64, 6: np.int32, 9: np.bool_}[a["to"]])
+    if op == "Slice":
+        data = np.asarray(x[0])
+        starts, ends = np.atleast_1d(x[1]), np.atleast_1d(x[2])
+        axes = np.atleast_1d(x[3]) if len(x) > 3 and x[3] is not None else np.arange(len(starts))
+        steps = np.atleast_1d(x[4]) if len(x) > 4 and x[4] is not None else np.ones(len(starts), np.int64)
+        idx = [slice(None)] * data.ndim
+        for s, e, ax, st in zip(starts, ends, axes, steps):
+            idx[int(ax)] = slice(int(s), int(min(e, np.iinfo(np.int64).max)), int(st))
+        return data[tuple(idx)]
+    raise LoweringError("cannot fold %s" % op)
+
+
+class _T:
+    """A logical NCHW tensor during lowering."""
+    __slots__ = ("C", "H", "W", "home", "view", "scaled", "dtype")
+
+    def __init__(self, C, H, W):
+        self.C, self.H, self.W = C, H, W
+        self.home = None      # (parent tensor name, c_off, c_stride) if it lives inside another tensor
+        self.view = None
+        self.scaled = None    # ('c', x, gate) / ('s', x, gate): lazily applied SE / sSE multiply
+        self.dtype = P.DT_F32
+
+
+_ACT_AFTER = {"Relu": P.ACT_RELU}
+
+
+class _Lowerer:
+    def __init__(self, graph, name, in_hw, input_u8=True):
+        self.g = graph
+        self.plan = P.Plan(name)
+        self.nodes = graph.nodes
+        self.vals = dict(graph.weights)       # name -> numpy constant
+        self.t = {}                           # name -> _T
+        self.uses = {}
+        for i, n in enumerate(self.nodes):
+            for x in n.inputs:
+                self.uses.setdefault(x, []).append(i)
+        self.absorbed = set()                 # node indices consumed by a fusion
+        self.fused = {}                       # conv node idx -> dict(act, out, res)
+        self.pending_copies = {}              # node idx -> [(src tensor, dst tensor)]
+        self.in_hw = in_hw
+        self.input_u8 = input_u8
+        self.decode_derived = set()
+        self.det_heads = []
+
+    # ------------------------------------------------------------------ helpers
+    def users(self, name):
+        return [self.nodes[i] for i in self.uses.get(name, [])]
+
+    def user_idx(self, name):
+        return self.uses.get(name, [])
+
+    def is_const(self, name):
+        return name in self.vals
+
+    def shape_of(self, name):
+        t = self.t[name]
+        return [1, t.C, t.H, t.W]
+
+    # ------------------------------------------------------------------ pass A: shapes, fusions, homes
+    def analyse(self):
+        g = self.g
+        inp = g.inputs[0]
+        self.t[inp] = _T(3, self.in_hw[0], self.in_hw[1])
+        self.input_name = inp
+        for idx, n in enumerate(self.nodes):
+            if idx in self.absorbed:
+                continue
+            self._analyse_node(idx, n)
+
+    def _set(self, name, C, H, W):
+        self.t[name] = _T(C, H, W)
+        return self.t[name]
+
+    def _analyse_node(self, idx, n):
+        op = n.op
+        if op == "Constant":
+            self.vals[n.outputs[0]] = np.asarray(n.attrs["value"])
+            return
+        ins = n.inputs
+        if any(i in self.decode_derived for i in ins):
+            self.decode_derived.update(n.outputs)
+            return
+        if op == "Shape" and ins[0] in self.t:
+            self.vals[n.outputs[0]] = np.array(self.shape_of(ins[0]), np.int64)
+            return
+        if all((i == "" or i in self.vals) for i in ins) and op not in ("Conv",):
+            if op == "ConstantOfShape" or op == "Equal" or op == "Where" or op == "Expand":
+                self.decode_derived.update(n.outputs)   # only appears inside decode tails
+                return
+            self.vals[n.outputs[0]] = _fold(n, self.vals)
+            return
+        x = self.t.get(ins[0])
+        if op == "Conv":
+            w = self.vals[ins[1]]
+            a = n.attrs
+            k, s, d, p = a["kernel_shape"], a["strides"], a["dilations"], a["pads"]
+            Ho = (x.H + 2 * p[0] - d[0] * (k[0] - 1) - 1) // s[0] + 1
+            Wo = (x.W + 2 * p[1] - d[1] * (k[1] - 1) - 1) // s[1] + 1
+            out = n.outputs[0]
+            self._set(out, w.shape[0], Ho, Wo)
+            self._fuse_after_conv(idx, n, out)
+            return
+        if op in ("Relu", "Sigmoid", "HardSigmoid"):
+            # stand-alone activation not fused into a conv: only BatchNormalization->Relu here
+            self._set(n.outputs[0], x.C, x.H, x.W)
+            return
+        if op == "BatchNormalization":
+            self._set(n.outputs[0], x.C, x.H, x.W)
+            us = self.user_idx(n.outputs[0])
+            if len(us) == 1 and self.nodes[us[0]].op == "Relu":
+                self.absorbed.add(us[0])
+                self.fused[idx] = dict(act=P.ACT_RELU, out=self.nodes[us[0]].outputs[0])
+                self._set(self.nodes[us[0]].outputs[0], x.C, x.H, x.W)
+            else:
+                self.fused[idx] = dict(act=P.ACT_NONE, out=n.outputs[0])
+            return
+        if op in ("ReduceMean", "GlobalAveragePool"):
+            if op == "ReduceMean":
+                assert sorted(n.attrs["axes"]) == [2, 3] and n.attrs.get("keepdims", 1) == 1
+            self._set(n.outputs[0], x.C, 1, 1)
+            return
+        if op == "MaxPool":
+            assert n.attrs["kernel_shape"] == [2, 2] and n.attrs["strides"] == [2, 2] and n.attrs.get("ceil_mode", 0) == 1
+            self._set(n.outputs[0], x.C, -(-x.H // 2), -(-x.W // 2))
+            return
+        if op == "Resize":
+            if len(ins) > 3 and ins[3] != "" and np.asarray(self.vals[ins[3]]).size > 0:
+                size = [int(v) for v in np.asarray(self.vals[ins[3]]).reshape(-1)[2:]]
+            else:
+                sc = np.asarray(self.vals[ins[2]]).reshape(-1)
+                size = [int(np.floor(x.H * sc[2])), int(np.floor(x.W * sc[3]))]
+            self._set(n.outputs[0], x.C, size[0], size[1])
+            return
+        if op == "Mul":
+            a_, b_ = self.t.get(ins[0]), self.t.get(ins[1])
+            if a_ is None or b_ is None:
+                raise LoweringError("Mul with constant operand outside decode: %s" % n.name)
+            big, small = (ins[0], ins[1]) if (a_.H * a_.W * a_.C >= b_.H * b_.W * b_.C) else (ins[1], ins[0])
+            tb, ts = self.t[big], self.t[small]
+            o = self._set(n.outputs[0], tb.C, tb.H, tb.W)
+            if ts.H == 1 and ts.W == 1 and ts.C == tb.C:
+                o.scaled = ("c", big, small)
+            elif ts.C == 1 and ts.H == tb.H and ts.W == tb.W:
+                o.scaled = ("s", big, small)
+            else:
+                raise LoweringError("unsupported Mul %s" % n.name)
+            return
+        if op == "Add":
+            a_, b_ = self.t[ins[0]], self.t[ins[1]]
+            if a_.scaled and b_.scaled and a_.scaled[1] == b_.scaled[1] and {a_.scaled[0], b_.scaled[0]} == {"c", "s"}:
+                self._set(n.outputs[0], a_.C, a_.H, a_.W)
+                return
+            raise LoweringError("unfused Add %s" % n.name)
+        if op == "Concat":
+            assert n.attrs["axis"] == 1
+            parts = [self.t[i] for i in ins]
+            C = sum(p.C for p in parts)
+            out = n.outputs[0]
+            shuffle = self._match_shuffle(idx, out, C, parts[0].H, parts[0].W)
+            if shuffle is not None:
+                out = shuffle
+                assert len(parts) == 2 and parts[0].C == parts[1].C
+            self._set(out, C, parts[0].H, parts[0].W)
+            off = 0
+            copies = []
+            for gi, (nm, p) in enumerate(zip(ins, parts)):
+                spec = (out, gi, 2) if shuffle is not None else (out, off, 1)
+                if p.home is None and nm != self.input_name and not self._is_alias(nm):
+                    p.home = spec
+                else:
+                    copies.append((nm, spec, p.C))
+                off += p.C
+            if copies:
+                self.pending_copies[idx] = copies
+            return
+        if op == "Slice":
+            starts = np.atleast_1d(self.vals[ins[1]])
+            ends = np.atleast_1d(self.vals[ins[2]])
+            axes = np.atleast_1d(self.vals[ins[3]]) if len(ins) > 3 else np.array([0])
+            assert len(starts) == 1 and int(axes[0]) == 1
+            s, e = int(starts[0]), int(min(int(ends[0]), x.C))
+            o = self._set(n.outputs[0], e - s, x.H, x.W)
+            o.home = (ins[0], s, 1)
+            self.alias = getattr(self, "alias", set())
+            self.alias.add(n.outputs[0])
+            return
+        if op == "Reshape" and ins[0] in self.t:
+            shape = [int(v) for v in np.asarray(self.vals[ins[1]]).reshape(-1)]
+            if len(shape) == 5 and shape[1] == 3 and shape[2] == 16:
+                # Detect head: everything downstream is the decode tail
+                self.det_heads.append(ins[0])
+                self.decode_derived.update(n.outputs)
+                return
+            raise LoweringError("unsupported Reshape %s -> %s" % (n.name, shape))
+        raise LoweringError("unsupported op %s (%s)" % (op, n.name))
+
+    def _is_alias(self, nm):
+        return nm in getattr(self, "alias", set())
+
+    def _match_shuffle(self, idx, out, C, H, W):
+        us = self.user_idx(out)
+        if len(us) != 1 or self.nodes[us[0]].op != "Reshape":
+            return None
+        r1 = self.nodes[us[0]]
+        # the reshape target is a Constant node that may come later in file order
+        shp = self._const_of(r1.inputs[1])
+        if shp is None or list(shp) != [1, 2, C // 2, H, W]:
+            return None
+        u2 = self.user_idx(r1.outputs[0])
+        tr = self.nodes[u2[0]]
+        if len(u2) != 1 or tr.op != "Transpose" or tr.attrs["perm"] != [0, 2, 1, 3, 4]:
+            return None
+        u3 = self.user_idx(tr.outputs[0])
+        r2 = self.nodes[u3[0]]
+        shp2 = self._const_of(r2.inputs[1])
+        if len(u3) != 1 or r2.op != "Reshape" or list(shp2) not in ([1, C, H, W], [1, -1, H, W]):
+            return None
+        self.absorbed.update([us[0], u2[0], u3[0]])
+        return r2.outputs[0]
+
+    def _const_of(self, name):
+        if name in self.vals:
+            return np.asarray(self.vals[name]).reshape(-1)
+        for n in self.nodes:
+            if n.op == "Constant" and n.outputs[0] == name:
+                return np.asarray(n.attrs["value"]).reshape(-1)
+        return None
+
+    def _fuse_after_conv(self, idx, n, out):
+        t = self.t[out]
+        us = self.user_idx(out)
+        ops = sorted(self.nodes[u].op for u in us)
+        act, cur = P.ACT_NONE, out
+        if ops == ["Slice"] * 3 and any(m.op == "ArgMax" for m in self.nodes):
+            # heat-map head: the three Slices start the arg-max decode tail
+            for u in us:
+                self.absorbed.add(u)
+                self.decode_derived.update(self.nodes[u].outputs)
+            self.fused[idx] = dict(act=P.ACT_NONE, out=out, res=None)
+            return
+        if ops == ["Relu"]:
+            act, cur = P.ACT_RELU, self.nodes[us[0]].outputs[0]
+            self.absorbed.add(us[0])
+        elif ops in (["Mul", "Sigmoid"], ["HardSigmoid", "Mul"]):
+            gate = [u for u in us if self.nodes[u].op != "Mul"][0]
+            mul = [u for u in us if self.nodes[u].op == "Mul"][0]
+            gout = self.nodes[gate].outputs[0]
+            if sorted(self.nodes[mul].inputs) == sorted([out, gout]) and self.user_idx(gout) == [mul]:
+                act = P.ACT_SILU if self.nodes[gate].op == "Sigmoid" else P.ACT_HSWISH
+                if act == P.ACT_HSWISH:
+                    self._check_hsig(self.nodes[gate])
+                cur = self.nodes[mul].outputs[0]
+                self.absorbed.update([gate, mul])
+        elif ops == ["Sigmoid"]:
+            act, cur = P.ACT_SIGMOID, self.nodes[us[0]].outputs[0]
+            self.absorbed.add(us[0])
+        elif ops == ["HardSigmoid"]:
+            self._check_hsig(self.nodes[us[0]])
+            act, cur = P.ACT_HSIGMOID, self.nodes[us[0]].outputs[0]
+            self.absorbed.add(us[0])
+        res = None
+        u2 = self.user_idx(cur)
+        if len(u2) == 1 and self.nodes[u2[0]].op == "Add":
+            add = self.nodes[u2[0]]
+            other = [i for i in add.inputs if i != cur]
+            if len(other) == 1 and other[0] in self.t and not self.t[other[0]].scaled:
+                o = self.t[other[0]]
+                if (o.C, o.H, o.W) == (t.C, t.H, t.W):
+                    res = other[0]
+                    self.absorbed.add(u2[0])
+                    cur = add.outputs[0]
+        if cur != out:
+            self._set(cur, t.C, t.H, t.W)
+        self.fused[idx] = dict(act=act, out=cur, res=res)
+
+    @staticmethod
+    def _check_hsig(node):
+        al = node.attrs.get("alpha", 0.2)
+        be = node.attrs.get("beta", 0.5)
+        if abs(al - 1.0 / 6.0) > 1e-6 or be != 0.5:
+            raise LoweringError("HardSigmoid alpha/beta %r/%r" % (al, be))
+
+    # ------------------------------------------------------------------ views
+    def view(self, name):
+        t = self.t[name]
+        if t.view is not None:
+            return t.view
+        if t.home is not None:
+            parent, off, stride = t.home
+            t.view = self.view(parent).sub(off, t.C, stride)
+        else:
+            b = self.plan.new_buf(t.C, t.H, t.W, t.dtype, name)
+            t.view = P.View(b, 0, 1, t.C)
+        return t.view
+
+    # ------------------------------------------------------------------ pass B: emission
+    def emit(self):
+        pl = self.plan
+        tin = self.t[self.input_name]
+        tin.dtype = P.DT_U8 if self.input_u8 else P.DT_F32
+        pl.input = self.view(self.input_name)
+        for idx, n in enumerate(self.nodes):
+            if idx in self.absorbed or n.op == "Constant":
+                continue
+            if any(i in self.decode_derived for i in n.inputs) or n.outputs[0] in self.decode_derived:
+                continue
+            if n.outputs[0] in self.vals:
+                continue
+            self._emit_node(idx, n)
+            if getattr(self, "done", False):
+                break
+        if self.det_heads:
+            self._emit_det_decode()
+
+    def _conv_input(self, name):
+        """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
+        t = self.t[name]
+        if t.scaled:
+            kind, x, gate = t.scaled
+            if kind != "c":
+                raise LoweringError("sSE-scaled tensor feeding a conv")
+            return self.view(x), self.view(gate)
+        return self.view(name), None
+
+    def _emit_node(self, idx, n):
+        pl, op = self.plan, n.op
+        ins = n.inputs
+        if op == "Conv":
+            f = self.fused[idx]
+            a = n.attrs
+            w = self.vals[ins[1]].astype(np.float32)
+            b = self.vals[ins[2]].astype(np.float32) if len(ins) > 2 else None
+            k, s, d, p = a["kernel_shape"], a["strides"], a["dilations"], a["pads"]
+            assert p[0] == p[2] and p[1] == p[3]
+            groups = a.get("group", 1)
+            xin, gate = self._conv_input(ins[0])
+            out_t = self.t[f["out"]]
+            # heat-map head: fuse the decode tail instead of materialising the output tensor name
+            out_v = self.view(f["out"])
+            flags = 0
+            if ins[0] == self.input_name and self.input_u8:
+                flags |= P.FLAG_IN_U8
+            assert xin.c_stride == 1, "strided input view"
+            if groups == 1:
+                wk = np.ascontiguousarray(w.transpose(0, 2, 3, 1))      # [Cout][kh][kw][Cin]
+                res = self.view(f["res"]) if f.get("res") else None
+                o = P.Op(P.OP_CONV, [xin, res, gate], [out_v], f["act"], k, s, p[:2], d, wk, b, flags,
+                         name=n.name)
+                pl.macs += out_t.C * out_t.H * out_t.W * w.shape[1] * k[0] * k[1]
+            else:
+                assert groups == w.shape[0] and w.shape[1] == 1 and gate is None and not f.get("res")
+                wk = np.ascontiguousarray(w.reshape(w.shape[0], -1).T)    # [kh*kw][C]
+                o = P.Op(P.OP_DWCONV, [xin], [out_v], f["act"], k, s, p[:2], d, wk,
+                         b if b is not None else np.zeros(w.shape[0], np.float32), flags, name=n.name)
+                pl.macs += out_t.C * out_t.H * out_t.W * k[0] * k[1]
+            pl.ops.append(o)
+            self._maybe_hm_decode(f["out"])
+            return
+        if op in ("ReduceMean", "GlobalAveragePool"):
+            pl.ops.append(P.Op(P.OP_GAP, [self.view(ins[0])], [self.view(n.outputs[0])], name=n.name))
+            return
+        if op == "MaxPool":
+            pl.ops.append(P.Op(P.OP_MAXPOOL2, [self.view(ins[0])], [self.view(n.outputs[0])], name=n.name))
+            return
+        if op == "Resize":
+            a = n.attrs
+            src, dst = self.view(ins[0]), self.view(n.outputs[0])
+            if a["mode"] == "nearest":
+                assert a["coordinate_transformation_mode"] == "asymmetric" and a["nearest_mode"] == "floor"
+                pl.ops.append(P.Op(P.OP_RESIZE_NEAREST, [src], [dst], name=n.name))
+            else:
+                assert a["mode"] == "linear" and a["coordinate_transformation_mode"] == "half_pixel"
+                assert dst.H == 2 * src.H and dst.W == 2 * src.W
+                pl.ops.append(P.Op(P.OP_UPSAMPLE_BILINEAR2X, [src], [dst], name=n.name))
+            return
+        if op == "BatchNormalization":
+            f = self.fused[idx]
+            sc, bi, mean, var = [self.vals[i].astype(np.float32) for i in ins[1:5]]
+            eps = np.float32(n.attrs.get("epsilon", 1e-5))
+            inv = (sc / np.sqrt(var + eps)).astype(np.float32)
+            shift = (bi - mean * inv).astype(np.float32)
+            pl.ops.append(P.Op(P.OP_AFFINE_ACT, [self.view(ins[0])], [self.view(f["out"])], f["act"],
+                               w=inv, b=shift, name=n.name))
+            return
+        if op == "Concat":
+            for src, spec, C in self.pending_copies.get(idx, []):
+                parent, off, stride = spec
+                dst = self.view(parent).sub(off, C, stride)
+                pl.ops.append(P.Op(P.OP_COPY, [self.view(src)], [dst], name=n.name + ":copy"))
+            return
+        if op == "Mul":
+            return      # lazily-applied SE / scSE scale
+        if op == "Add":
+            a_, b_ = self.t[ins[0]], self.t[ins[1]]
+            c_t, s_t = (a_, b_) if a_.scaled[0] == "c" else (b_, a_)
+            x = c_t.scaled[1]
+            pl.ops.append(P.Op(P.OP_SCSE, [self.view(x), self.view(c_t.scaled[2]), self.view(s_t.scaled[2])],
+                               [self.view(n.outputs[0])], name=n.name))
+            return
+        if op == "Slice":
+            return
+        raise LoweringError("emit: unsupported %s %s" % (op, n.name))
+
+    # ------------------------------------------------------------------ decode tails
+    def _maybe_hm_decode(self, name):
+        us = self.users(name)
+        if not us or not all(u.op == "Slice" for u in us) or len(us) != 3:
+            return
+        if not any(n.op == "ArgMax" for n in self.nodes):
+            return
+        t = self.t[name]
+        bounds = sorted(int(np.atleast_1d(self._const_of(u.inputs[1]))[0]) for u in us)
+        npts = bounds[1]
+        if bounds != [0, npts, 2 * npts] or t.C != 3 * npts:
+            raise LoweringError("unexpected heat-map slicing %s" % bounds)
+        mods = [n for n in self.nodes if n.op == "Mod"]
+        side = int(np.asarray(self._const_of(mods[0].inputs[1])).reshape(-1)[0])
+        if side != t.W or t.H != t.W:
+            raise LoweringError("heat-map side %d vs %dx%d" % (side, t.H, t.W))
+        pl = self.plan
+        xy = pl.new_buf(2 * npts, 1, 1, P.DT_F32, "output")
+        sc = pl.new_buf(npts, 1, 1, P.DT_F32, "score")
+        vxy, vsc = P.View(xy, 0, 1, 2 * npts), P.View(sc, 0, 1, npts)
+        pl.ops.append(P.Op(P.OP_HM_DECODE, [self.view(name)], [vxy, vsc], ints=[npts], name="hm_decode"))
+        # graph outputs are ['output' (1,196), 'score' (1,98)] in that order
+        assert len(self.g.outputs) == 2
+        pl.outputs = [vxy, vsc]
+        self.done = True
+
+    def _emit_det_decode(self):
+        pl = self.plan
+        assert len(self.det_heads) == 3
+        views = [self.view(h) for h in self.det_heads]
+        consts = []
+        rows = 0
+        for h in self.det_heads:
+            t = self.t[h]
+            stride, anchors = self._det_constants(h, t)
+            consts += [stride] + anchors
+            rows += 3 * t.H * t.W
+        out = pl.new_buf(16, rows, 1, P.DT_F32, "output")     # (N, rows, 16) stored as H=rows, W=1, C=16
+        ov = P.View(out, 0, 1, 16)
+        pl.ops.append(P.Op(P.OP_DET_DECODE, views, [ov], w=np.array(consts, np.float32), ints=[rows],
+                           name="det_decode"))
+        pl.outputs = [ov]
+
+    def _det_constants(self, head, t):
+        """Dig stride and the three (w,h) anchors of one scale out of the Detect tail's constants."""
+        # nodes downstream of this head until the next head
+        start = [i for i, n in enumerate(self.nodes) if head in n.inputs][0]
+        stride, anchors, grid_ok = None, None, False
+        i = start
+        seen_pow = False
+        while i < len(self.nodes):
+            n = self.nodes[i]
+            if n.op == "Conv":
+                break
+            if n.op == "Pow":
+                seen_pow = True
+                mul = self.nodes[self.user_idx(n.outputs[0])[0]]
+                c = [self._const_full(x) for x in mul.inputs if self._const_full(x) is not None][0]
+                assert c.shape == (1, 3, t.H, t.W, 2) and np.ptp(c, axis=(2, 3)).max() == 0
+                anchors = [float(v) for v in c[0, :, 0, 0, :].reshape(-1)]
+            if n.op == "Sub" and stride is None:
+                add = self.nodes[self.user_idx(n.outputs[0])[0]]
+                grid = [self._const_full(x) for x in add.inputs if self._const_full(x) is not None][0]
+                gx, gy = np.meshgrid(np.arange(t.W), np.arange(t.H))
+                assert np.array_equal(grid[0, 0, :, :, 0], gx) and np.array_equal(grid[0, 2, :, :, 1], gy)
+                grid_ok = True
+                mul = self.nodes[self.user_idx(add.outputs[0])[0]]
+                sc = [self._const_full(x) for x in mul.inputs if self._const_full(x) is not None][0]
+                stride = float(np.asarray(sc).reshape(-1)[0])
+            i += 1
+        if not (seen_pow and grid_ok and stride and anchors):
+            raise LoweringError("could not recover Detect constants for %s" % head)
+        return stride, anchors
+
+    def _const_full(self, name):
+        if name in self.vals:
+            return np.asarray(self.vals[name])
+        for n in self.nodes:
+            if n.op == "Constant" and n.outputs[0] == name:
+                return np.asarray(n.attrs["value"])
+        return None
+
+
+def lower(onnx_path, in_hw, name=None, input_u8=True):
+    """Build the plan for one of the reference's graphs at a fixed input size."""
+    g = load_onnx(onnx_path)
+    lw = _Lowerer(g, name or onnx_path, in_hw, input_u8)
+    lw.analyse()
+    lw.emit()
+    if not lw.plan.outputs:
+        raise LoweringError("no outputs produced for %s" % onnx_path)
+    return lw.plan

@@ -1,0 +1,155 @@
+"""Execution plan: the flat op list the CUDA engine (csrc/engine.cu) runs.
+
+A plan is what `lowering.lower()` makes out of one of the reference's .onnx files:
+  * buffers  — NHWC activations in HBM (float32, or uint8 for the network input),
+               sized per sample; the engine allocates them for `max_batch`.
+  * views    — (buffer, channel offset, channel stride, C, H, W).  Concat, Slice and
+               the ShuffleNetV2 channel shuffle never move data: producers write
+               through a view straight into the consumer's buffer.
+  * ops      — fused kernels (conv+bias+act+residual, depthwise, decode, ...).
+  * weights  — one float32 blob; ops carry offsets into it.
+
+`Plan.serialize()` produces the int32 words + float blob handed through the C-ABI
+(include/skps_b200.h: skps_engine_create).
+"""
+import numpy as np
+
+# ---- op types (keep in sync with csrc/plan.h) ------------------------------------
+OP_CONV = 1           # dense conv (any k/stride/dilation), +bias +act +residual, optional per-(n,cin) input scale
+OP_DWCONV = 2         # depthwise conv +bias +act
+OP_MAXPOOL2 = 3       # 2x2 stride 2, ceil_mode
+OP_RESIZE_NEAREST = 4  # asymmetric/floor nearest to the output view's H,W
+OP_UPSAMPLE_BILINEAR2X = 5  # half_pixel bilinear x2
+OP_COPY = 6           # channel-view copy
+OP_GAP = 7            # global average pool -> (N,1,1,C)
+OP_AFFINE_ACT = 8     # per-channel x*s+t then act (explicit BatchNormalization)
+OP_SCSE = 9           # x*cse[n,c] + x*sse[n,h,w]
+OP_DET_DECODE = 10    # yolov5-face head decode -> (N,rows,16)
+OP_HM_DECODE = 11     # heat-map argmax + offset decode -> (N,196),(N,98)
+
+OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
+
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SILU, ACT_SIGMOID, ACT_HSIGMOID = range(6)
+
+DT_F32, DT_U8 = 0, 1
+
+OP_WORDS = 64
+VIEW_WORDS = 6
+BUF_WORDS = 4
+
+
+class Buf:
+    def __init__(self, idx, C, H, W, dtype=DT_F32, name=""):
+        self.idx, self.C, self.H, self.W, self.dtype, self.name = idx, C, H, W, dtype, name
+
+    @property
+    def elems(self):
+        return self.C * self.H * self.W
+
+
+class View:
+    """Channel window onto a buffer.  Logical channel j lives at c_off + j*c_stride."""
+
+    def __init__(self, buf, c_off, c_stride, C):
+        self.buf, self.c_off, self.c_stride, self.C = buf, c_off, c_stride, C
+
+    @property
+    def H(self):
+        return self.buf.H
+
+    @property
+    def W(self):
+        return self.buf.W
+
+    def sub(self, off, C, stride=1):
+        return View(self.buf, self.c_off + off * self.c_stride, self.c_stride * stride, C)
+
+    def words(self):
+        return [self.buf.idx, self.c_off, self.c_stride, self.C, self.buf.H, self.buf.W]
+
+    def __repr__(self):
+        return "V(b%d[%d:+%d*%d] %dx%dx%d)" % (self.buf.idx, self.c_off, self.C, self.c_stride,
+                                                self.buf.H, self.buf.W, self.buf.C)
+
+
+_NOVIEW = [-1, 0, 1, 0, 0, 0]
+
+
+class Op:
+    def __init__(self, type, ins, outs, act=ACT_NONE, k=(1, 1), s=(1, 1), p=(0, 0), d=(1, 1),
+                 w=None, b=None, flags=0, ints=(), floats=(), name=""):
+        self.type, self.ins, self.outs, self.act = type, list(ins), list(outs), act
+        self.k, self.s, self.p, self.d = k, s, p, d
+        self.w, self.b = w, b                # numpy float32 arrays (already in kernel layout) or None
+        self.flags, self.ints, self.floats, self.name = flags, list(ints), list(floats), name
+        self.w_off = self.b_off = -1
+
+    def __repr__(self):
+        return "%s %s -> %s act=%d k=%s s=%s d=%s %s" % (OP_NAMES[self.type], self.ins, self.outs,
+                                                         self.act, self.k, self.s, self.d, self.name)
+
+
+FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
+
+
+class Plan:
+    def __init__(self, name):
+        self.name = name
+        self.bufs = []
+        self.ops = []
+        self.input = None        # View of the network input (uint8 NHWC)
+        self.outputs = []        # Views of the outputs
+        self.macs = 0            # conv MACs per sample (algorithmic work)
+
+    def new_buf(self, C, H, W, dtype=DT_F32, name=""):
+        b = Buf(len(self.bufs), C, H, W, dtype, name)
+        self.bufs.append(b)
+        return b
+
+    # ------------------------------------------------------------------ serialization
+    def pack_weights(self):
+        """Concatenate all op weights/biases into one float32 blob (16-byte aligned pieces)."""
+        parts = []
+        off = 0
+
+        def put(a):
+            nonlocal off
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+            pad = (-a.size) % 4
+            start = off
+            parts.append(a)
+            if pad:
+                parts.append(np.zeros(pad, np.float32))
+            off += a.size + pad
+            return start
+        for op in self.ops:
+            op.w_off = put(op.w) if op.w is not None else -1
+            op.b_off = put(op.b) if op.b is not None else -1
+        return np.concatenate(parts) if parts else np.zeros(4, np.float32)
+
+    def serialize(self):
+        blob = self.pack_weights()
+        bw = []
+        for b in self.bufs:
+            bw += [b.C, b.H, b.W, b.dtype]
+        ow = []
+        for op in self.ops:
+            w = [op.type, op.act]
+            for i in range(3):
+                w += op.ins[i].words() if i < len(op.ins) and op.ins[i] is not None else _NOVIEW
+            for i in range(2):
+                w += op.outs[i].words() if i < len(op.outs) else _NOVIEW
+            w += [op.k[0], op.k[1], op.s[0], op.s[1], op.p[0], op.p[1], op.d[0], op.d[1]]
+            w += [op.w_off, op.b_off, op.flags]
+            ints = list(op.ints) + [0] * (4 - len(op.ints))
+            w += ints[:4]
+            fl = np.asarray(list(op.floats) + [0.0] * (8 - len(op.floats)), np.float32)[:8]
+            w += fl.view(np.int32).tolist()
+            assert len(w) <= OP_WORDS, len(w)
+            w += [0] * (OP_WORDS - len(w))
+            ow += w
+        header = np.array([0x534B5053, 1, len(self.bufs), len(self.ops),
+                           self.input.buf.idx, len(self.outputs)] +
+                          [v.buf.idx for v in self.outputs] + [0] * (2 - len(self.outputs)), np.int32)
+        words = np.concatenate([header, np.array(bw, np.int32), np.array(ow, np.int32)])
+        return words, blob
