@@ -60,8 +60,9 @@ static TView resolve(const skps_engine* e, const View& v) {
     return t;
 }
 
-static int run_ops(skps_engine* e, int batch, cudaStream_t s) {
-    for (size_t i = 0; i < e->ops.size(); ++i) {
+static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int last = -1) {
+    const size_t end = last < 0 ? e->ops.size() : (size_t)last;
+    for (size_t i = (size_t)first; i < end; ++i) {
         const OpDesc& op = e->ops[i];
         TView in0 = resolve(e, op.in[0]), in1 = resolve(e, op.in[1]), in2 = resolve(e, op.in[2]);
         TView out0 = resolve(e, op.out[0]), out1 = resolve(e, op.out[1]);
@@ -210,6 +211,13 @@ extern "C" SKPS_API int skps_engine_read_buffer(skps_engine* e, int buf, int bat
     return 0;
 }
 extern "C" SKPS_API int skps_engine_launches_per_forward(const skps_engine* e) { return e ? e->launches : 0; }
+
+extern "C" SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int batch, void* stream) {
+    SKPS_CHECK(e && op_index >= 0 && op_index < (int)e->ops.size(), "run_op: bad op index");
+    SKPS_CHECK(batch > 0 && batch <= e->max_batch, "run_op: batch %d outside 1..%d", batch, e->max_batch);
+    SKPS_CUDA(cudaSetDevice(e->device));
+    return run_ops(e, batch, (cudaStream_t)stream, op_index, op_index + 1);
+}
 
 // Enqueue the op sequence (through a cached CUDA graph when possible).
 static int enqueue(skps_engine* e, int batch, cudaStream_t s) {
