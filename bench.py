@@ -35,6 +35,26 @@ STUDENT_README_GFLOP = 1.39e9                   # README "Flops(G)" convention (
 WORKLOAD = "student256_landmark_only_batch256"
 
 
+def log(msg):
+    sys.stderr.write("[bench %.1fs] %s\n" % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
+def host_cores():
+    """CPU threads this process may actually use: affinity mask capped by the cgroup quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -95,7 +115,7 @@ def cpu_reference_faces_per_s(n_faces, seed=0):
     import torch
     import frames
     from oracle.faceana_ref import LandmarkRef
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(host_cores())
     crops = frames.noise_crops(n_faces, seed=seed)
     ref = LandmarkRef()
     ref.forward_crops(crops[:2])                       # warm-up
@@ -121,7 +141,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_faces_per_step": sample},
-        "cpu_baseline": {"value": fps, "unit": "faces/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": fps, "unit": "faces/s", "cores": host_cores(), "kind": "port",
                          "sample": "%d faces per step, batch-1 loop, torch-CPU executor of kps_student.onnx" % sample},
         "e2e": {"value": fps, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -170,6 +190,7 @@ def main():
     dev_sets = [h.cuda(non_blocking=True) for h in host_sets]
     outs = [torch.empty((B, e), dtype=torch.float32, device="cuda") for e in eng.out_elems]
     torch.cuda.synchronize()
+    log("engine + inputs ready")
 
     def step_device(i):
         eng.forward_device(dev_sets[i % n_sets], outs, stream)
@@ -201,6 +222,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     faces_per_s = world * B * args.steps / (ms * 1e-3)
+    log("device-resident: %.1f faces/s (%.3f ms/step)" % (faces_per_s, ms / args.steps))
 
     # ---- end to end through the operator call with host buffers (pinned), H2D + D2H inside the timed region
     e2e_steps = max(5, min(args.steps, 20))
@@ -218,6 +240,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_fps = world * B * e2e_steps / e2e_s
+    log("e2e: %.1f faces/s" % e2e_fps)
     h2d = B * 256 * 256 * 3
     d2h = B * (196 + 98) * 4
 
@@ -249,6 +272,7 @@ def main():
     peak_tf, peak_hbm, peak_src = measured_peaks()
     k_flops = 2.0 * best_macs * B
     achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
+    log("dominant kernel %.3f ms -> %.2f TFLOP/s" % (k_ms, achieved_tf))
     bop = eng.plan.ops[best]
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None,
@@ -262,9 +286,11 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        n = 96
+        log("cpu baseline on %d host threads" % host_cores())
+        v1, dt1 = cpu_reference_faces_per_s(8)
+        n = int(max(8, min(256, 12.0 * v1)))          # ~12 s of CPU work
         v, dt = cpu_reference_faces_per_s(n)
-        cpu = {"value": v, "unit": "faces/s", "cores": os.cpu_count(), "kind": "port",
+        cpu = {"value": v, "unit": "faces/s", "cores": host_cores(), "kind": "port",
                "sample": "%d faces, batch-1 loop (face_landmark.py:40-48), torch-CPU executor, %.1f s" % (n, dt)}
 
     line = {

@@ -86,6 +86,13 @@ SKPS_API int skps_engine_launches_per_forward(const skps_engine* e);
  * (bench.py times the dominant kernel with CUDA events around this call). */
 SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int batch, void* stream);
 
+/* Unit-test entry for the tcgen05 convolution kernel (csrc/conv_tc.cu): one 'same' conv on host
+ * data.  x float32 NHWC, w_hi/w_lo float16 (n_tiles*n_tile, K_pad) as packed by
+ * plan.pack_tc_weights, out float32 NHWC. */
+SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                                const float* bias, int Cout, int ksize, int dil, int act, int n_tile, int n_tiles,
+                                const float* residual, int out_split, float* out);
+
 /* ------------------------------------------------------------------ image kernels */
 
 /* FaceDetector.preprocess (face_detector.py:45-71): BGR->RGB, cv2.resize INTER_LINEAR

@@ -15,6 +15,7 @@ SOURCES = {
     "engine.cu": [],
     "pipeline.cu": [],
     "conv_simt.cu": [],
+    "conv_tc.cu": [],
     "ops_misc.cu": [],
     "image_ops.cu": ["-fmad=false"],     # float32/double expressions must round like numpy's
 }

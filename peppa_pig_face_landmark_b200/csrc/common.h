@@ -13,7 +13,7 @@ enum OpType {
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
-enum { DT_F32 = 0, DT_U8 = 1 };
+enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
 enum { FLAG_IN_U8 = 1 };
 enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
 

@@ -1,0 +1,491 @@
+// Dense convolution as a tcgen05 implicit GEMM (sm_100a): the landmark network's 1x1 and 3x3
+// (incl. dilated) convolutions, 96.7 % of its MACs.
+//
+//   C[M = N*H*W pixels][Cout] = sum over taps (ky,kx), ci of  A[pixel + tap][ci] * W[co][tap][ci]
+//
+// * Operands are float16 hi/lo pairs: v = hi + lo with hi = fp16(v), lo = fp16(v - hi) (22 mantissa
+//   bits).  Each K-step issues three kind::f16 MMAs into one fp32 TMEM accumulator:
+//   hi*hi + hi*lo + lo*hi.  Measured against the fp32 oracle this keeps landmarks within 6e-5 px
+//   (budget 1e-3 px); plain fp16/bf16/tf32 single-pass does not (0.02-0.5 px).  Tensor work issued is
+//   therefore 3x the algorithmic FLOPs.
+// * A tiles (128 pixels x 64 channels) are fetched by 4-D TMA straight from the NHWC activation:
+//   box (64 ch, bw, bh) with signed start coordinates, so the conv zero padding and dilation come
+//   from TMA out-of-bounds fill; no im2col buffer exists.  B tiles (n_tile x 64) come from the
+//   pre-split, K-padded weight matrix.  Both land in 128B-swizzled shared memory.
+// * Warp roles: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
+//   warps 4-7 epilogue (TMEM -> registers -> bias/act/residual -> global).  Persistent CTAs, one per
+//   SM, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "../../include/skps_b200.h"
+#include "common.h"
+#include "conv_tc.h"
+
+namespace skps {
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate, single CTA.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// Shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
+constexpr int TC_BK = 64;             // channels per k-block (one 128-byte swizzle atom of fp16)
+constexpr int A_TILE_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 4;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcK p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_tile_bytes = (uint32_t)p.n_tile * TC_BK * 2;
+    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tfull_bar[a]), 1);
+            mbar_init(smem_u32(&tempty_bar[a]), 4);          // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int kblocks = p.taps * p.cchunks;
+
+    if (warp == 0) {
+        // ================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
+                const int img = m_idx / p.tiles_per_img;
+                const int t = m_idx - img * p.tiles_per_img;
+                const int tiles_x = p.W / p.bw;
+                const int y0 = (t / tiles_x) * p.bh, x0 = (t % tiles_x) * p.bw;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(fb, stage_bytes);
+                    const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+                    const int ky = tap / p.kw, kx = tap - ky * p.kw;
+                    const int cx = x0 + kx * p.dil - p.pad, cy = y0 + ky * p.dil - p.pad;
+                    const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
+                    tma_load_4d(sa, &tmA_hi, fb, cc * TC_BK, cx, cy, img);
+                    tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, fb, cc * TC_BK, cx, cy, img);
+                    tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, fb, kb * TC_BK, n_idx * p.n_tile);
+                    tma_load_2d(sa + 2 * A_TILE_BYTES + b_tile_bytes, &tmB_lo, fb, kb * TC_BK, n_idx * p.n_tile);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=f16, K-major both, N = n_tile, M = 128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
+                    const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 32 >> 4);       // 16 fp16 = 32 bytes along K
+                        // small terms first, then the dominant hi*hi product
+                        umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                        umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                        umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));                // frees the smem stage when the MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(smem_u32(&tfull_bar[acc]));                      // accumulator ready for the epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================================== epilogue (warps 4-7 = TMEM lane quarters 0-3)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
+            const int img = m_idx / p.tiles_per_img;
+            const int t = m_idx - img * p.tiles_per_img;
+            const int tiles_x = p.W / p.bw;
+            const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
+            const long long pix = ((long long)img * p.H + y) * p.W + x;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            const int co_tile = n_idx * p.n_tile;
+            for (int c0 = 0; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 32) {
+                float v[32];
+                tmem_ld32(t_addr + (uint32_t)c0, v);
+                const int co0 = co_tile + c0;
+                const int nvalid = min(32, p.Cout - co0);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < nvalid) {
+                        float b = p.bias ? __ldg(p.bias + co0 + j) : 0.f;
+                        v[j] = apply_act(v[j] + b, p.act);
+                    }
+                }
+                if (p.res) {
+                    if (p.res_fmt == DT_SPLIT16) {
+                        const __half* rh = (const __half*)p.res + pix * p.res_ld + p.res_coff + co0;
+                        const __half* rl = rh + p.res_plane;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
+                    } else {
+                        const float* r = (const float*)p.res + pix * p.res_ld + p.res_coff + co0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) v[j] += r[j];
+                    }
+                }
+                if (p.out_fmt == DT_SPLIT16) {
+                    __half* oh = (__half*)p.out + pix * p.out_ld + p.out_coff;
+                    __half* ol = oh + p.out_plane;
+                    const bool vec = p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 7) == 0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (g * 8 >= nvalid) break;
+                        __half hh[8], ll[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float f = v[g * 8 + j];
+                            hh[j] = __float2half_rn(f);
+                            ll[j] = __float2half_rn(f - __half2float(hh[j]));
+                        }
+                        if (vec && g * 8 + 8 <= nvalid) {
+                            *reinterpret_cast<uint4*>(oh + co0 + g * 8) = *reinterpret_cast<const uint4*>(hh);
+                            *reinterpret_cast<uint4*>(ol + co0 + g * 8) = *reinterpret_cast<const uint4*>(ll);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (g * 8 + j < nvalid) {
+                                    oh[(long long)(co0 + g * 8 + j) * p.out_cstride] = hh[j];
+                                    ol[(long long)(co0 + g * 8 + j) * p.out_cstride] = ll[j];
+                                }
+                        }
+                    }
+                } else {
+                    float* o = (float*)p.out + pix * p.out_ld + p.out_coff;
+                    const bool vec = p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 3) == 0;
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (g * 4 >= nvalid) break;
+                        if (vec && g * 4 + 4 <= nvalid) {
+                            *reinterpret_cast<float4*>(o + co0 + g * 4) =
+                                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (g * 4 + j < nvalid) o[(long long)(co0 + g * 4 + j) * p.out_cstride] = v[g * 4 + j];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff) {
+    if (W < 8 || (Cin % 8) || (in_ld % 8) || (in_coff % 8)) return false;
+    if (W >= TC_BM) return W % TC_BM == 0;
+    if (TC_BM % W) return false;
+    return H % (TC_BM / W) == 0;
+}
+
+int tc_prepare(TcLayer& L, const TcSetup& s) {
+    EncodeTiledFn enc = get_encode();
+    SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+    SKPS_CHECK(tc_shape_ok(s.H, s.W, s.Cin, s.in_ld, s.in_coff), "conv_tc: unsupported shape %dx%d Cin=%d ld=%d off=%d",
+               s.H, s.W, s.Cin, s.in_ld, s.in_coff);
+    SKPS_CHECK(s.kh == s.kw && s.pad == s.dil * (s.kh - 1) / 2, "conv_tc: only 'same' square kernels");
+    L.k = TcK();
+    TcK& k = L.k;
+    k.H = s.H; k.W = s.W;
+    k.bw = s.W >= TC_BM ? TC_BM : s.W;
+    k.bh = TC_BM / k.bw;
+    k.tiles_per_img = (s.H / k.bh) * (s.W / k.bw);
+    k.taps = s.kh * s.kw; k.kw = s.kw; k.dil = s.dil; k.pad = s.pad;
+    k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;
+    k.Cout = s.Cout; k.act = s.act;
+    k.n_tile = s.n_tile; k.n_tiles = s.n_tiles;
+    const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
+    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
+    SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
+    L.smem_bytes = (int)(k.stages * stage_bytes + 1024);
+
+    // activations: (C, W, H, N) fp16, channel window [in_coff, in_coff+Cin) of rows of in_ld channels
+    for (int plane = 0; plane < 2; ++plane) {
+        cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
+        cuuint64_t strides[3] = {(cuuint64_t)s.in_ld * 2, (cuuint64_t)s.W * s.in_ld * 2, (cuuint64_t)s.H * s.W * s.in_ld * 2};
+        cuuint32_t box[4] = {TC_BK, (cuuint32_t)k.bw, (cuuint32_t)k.bh, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        void* base = (void*)((__half*)s.in_base + (plane ? s.in_plane : 0) + s.in_coff);
+        CUresult r = enc(plane ? &L.a_lo : &L.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
+    }
+    // weights: (K_pad, rows) fp16, rows = n_tiles*n_tile (zero rows beyond Cout)
+    const int K_pad = k.taps * k.cchunks * TC_BK;
+    for (int plane = 0; plane < 2; ++plane) {
+        cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)(k.n_tiles * k.n_tile)};
+        cuuint64_t strides[1] = {(cuuint64_t)K_pad * 2};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)k.n_tile};
+        cuuint32_t estr[2] = {1, 1};
+        void* base = (void*)(plane ? s.w_lo : s.w_hi);
+        CUresult r = enc(plane ? &L.b_lo : &L.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    }
+    k.bias = s.bias;
+    k.out = s.out; k.out_fmt = s.out_fmt; k.out_plane = s.out_plane; k.out_ld = s.out_ld; k.out_coff = s.out_coff;
+    k.out_cstride = s.out_cstride;
+    k.res = s.res; k.res_fmt = s.res_fmt; k.res_plane = s.res_plane; k.res_ld = s.res_ld; k.res_coff = s.res_coff;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    return 0;
+}
+
+int tc_launch(const TcLayer& L, int batch, int num_sms, cudaStream_t stream) {
+    TcK k = L.k;
+    k.m_tiles = batch * k.tiles_per_img;
+    int total = k.m_tiles * k.n_tiles;
+    int grid = total < num_sms ? total : num_sms;
+    conv_tc_kernel<<<grid, TC_THREADS, L.smem_bytes, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// float32 NHWC -> hi/lo float16 planes (used by the debug entry point and by f32->split conversions)
+__global__ void f32_to_split_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = src[i];
+    __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+}  // namespace skps
+
+using namespace skps;
+
+// Debug/unit-test entry: one conv through the tensor-core kernel on host data.
+//   x      [host] float32 NHWC (N,H,W,Cin)
+//   w_hi/w_lo [host] float16 (rows, K_pad) as packed by plan.py:pack_tc_weights
+//   out    [host] float32 NHWC (N,H,W,Cout)
+extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi,
+                                           const void* w_lo, const float* bias, int Cout, int ksize, int dil, int act,
+                                           int n_tile, int n_tiles, const float* residual, int out_split,
+                                           float* out) {
+    SKPS_CHECK(x && w_hi && w_lo && out, "debug_conv_tc: null argument");
+    const long long nin = (long long)N * H * W * Cin, nout = (long long)N * H * W * Cout;
+    const int cchunks = (Cin + TC_BK - 1) / TC_BK;
+    const size_t wbytes = (size_t)n_tiles * n_tile * ksize * ksize * cchunks * TC_BK * 2;
+    float *d_x = nullptr, *d_bias = nullptr, *d_out = nullptr, *d_res = nullptr;
+    __half *d_split = nullptr, *d_wh = nullptr, *d_wl = nullptr, *d_osplit = nullptr;
+    SKPS_CUDA(cudaMalloc(&d_x, nin * 4));
+    SKPS_CUDA(cudaMalloc(&d_split, nin * 4));
+    SKPS_CUDA(cudaMalloc(&d_wh, wbytes));
+    SKPS_CUDA(cudaMalloc(&d_wl, wbytes));
+    SKPS_CUDA(cudaMalloc(&d_out, nout * 4));
+    SKPS_CUDA(cudaMalloc(&d_osplit, nout * 4));
+    SKPS_CUDA(cudaMemcpy(d_x, x, nin * 4, cudaMemcpyHostToDevice));
+    SKPS_CUDA(cudaMemcpy(d_wh, w_hi, wbytes, cudaMemcpyHostToDevice));
+    SKPS_CUDA(cudaMemcpy(d_wl, w_lo, wbytes, cudaMemcpyHostToDevice));
+    if (bias) {
+        SKPS_CUDA(cudaMalloc(&d_bias, Cout * 4));
+        SKPS_CUDA(cudaMemcpy(d_bias, bias, Cout * 4, cudaMemcpyHostToDevice));
+    }
+    if (residual) {
+        SKPS_CUDA(cudaMalloc(&d_res, nout * 4));
+        SKPS_CUDA(cudaMemcpy(d_res, residual, nout * 4, cudaMemcpyHostToDevice));
+    }
+    f32_to_split_kernel<<<(unsigned)((nin + 255) / 256), 256>>>(d_x, d_split, d_split + nin, nin);
+    SKPS_CUDA(cudaGetLastError());
+    TcSetup s = {};
+    s.H = H; s.W = W; s.Cin = Cin; s.in_ld = Cin; s.in_coff = 0; s.max_batch = N;
+    s.in_base = d_split; s.in_plane = nin;
+    s.kh = s.kw = ksize; s.dil = dil; s.pad = dil * (ksize - 1) / 2;
+    s.Cout = Cout; s.act = act; s.n_tile = n_tile; s.n_tiles = n_tiles;
+    s.w_hi = d_wh; s.w_lo = d_wl; s.bias = d_bias;
+    s.out = out_split ? (void*)d_osplit : (void*)d_out; s.out_fmt = out_split ? DT_SPLIT16 : DT_F32;
+    s.out_plane = nout; s.out_ld = Cout; s.out_coff = 0; s.out_cstride = 1;
+    s.res = d_res; s.res_fmt = DT_F32; s.res_plane = 0; s.res_ld = Cout; s.res_coff = 0;
+    TcLayer L;
+    if (tc_prepare(L, s)) return 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (tc_launch(L, N, sms, 0)) return 1;
+    SKPS_CUDA(cudaDeviceSynchronize());
+    if (out_split) {
+        // recombine hi+lo on the host side of the test
+        __half* tmp = (__half*)malloc(nout * 4);
+        SKPS_CUDA(cudaMemcpy(tmp, d_osplit, nout * 4, cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < nout; ++i) out[i] = __half2float(tmp[i]) + __half2float(tmp[nout + i]);
+        free(tmp);
+    } else {
+        SKPS_CUDA(cudaMemcpy(out, d_out, nout * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_x); cudaFree(d_split); cudaFree(d_wh); cudaFree(d_wl); cudaFree(d_out); cudaFree(d_osplit);
+    if (d_bias) cudaFree(d_bias);
+    if (d_res) cudaFree(d_res);
+    return 0;
+}

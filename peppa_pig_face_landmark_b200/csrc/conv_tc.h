@@ -1,0 +1,39 @@
+// Host/device structs of the tcgen05 convolution path (conv_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace skps {
+
+struct TcK {                     // kernel parameters
+    int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
+    int taps, kw, dil, pad, cchunks;
+    int Cout, act, stages;
+    const float* bias;
+    void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
+    const void* res; int res_fmt; long long res_plane; int res_ld, res_coff;
+};
+
+struct TcLayer {                 // prepared once per conv op at engine creation
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    TcK k;
+    int smem_bytes;
+};
+
+struct TcSetup {
+    int H, W, Cin, in_ld, in_coff, max_batch;
+    const void* in_base; long long in_plane;      // hi plane base (fp16), lo plane = base + in_plane elements
+    int kh, kw, dil, pad;
+    int Cout, act, n_tile, n_tiles;
+    const void* w_hi; const void* w_lo;           // device, (n_tiles*n_tile, K_pad) fp16
+    const float* bias;
+    void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
+    const void* res; int res_fmt; long long res_plane; int res_ld, res_coff;
+};
+
+bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff);
+int tc_prepare(TcLayer& L, const TcSetup& s);
+int tc_launch(const TcLayer& L, int batch, int num_sms, cudaStream_t stream);
+
+}  // namespace skps

@@ -153,3 +153,35 @@ class Plan:
                           [v.buf.idx for v in self.outputs] + [0] * (2 - len(self.outputs)), np.int32)
         words = np.concatenate([header, np.array(bw, np.int32), np.array(ow, np.int32)])
         return words, blob
+
+
+# ---- tensor-core (tcgen05) convolution support ---------------------------------------------------
+TC_BK = 64            # channels per k-block (csrc/conv_tc.cu)
+
+
+def tc_tiling(cout):
+    """Split Cout into n_tiles equal UMMA-N tiles (multiple of 16, <= 256)."""
+    c16 = -(-cout // 16) * 16
+    n_tiles = -(-c16 // 256)
+    n_tile = -(-(-(-c16 // n_tiles)) // 16) * 16
+    return n_tile, n_tiles
+
+
+def split_fp16(a):
+    """v -> (hi, lo) float16 with v ~= hi + lo (22 significant bits)."""
+    a = np.asarray(a, dtype=np.float32)
+    hi = a.astype(np.float16)
+    lo = (a - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def pack_tc_weights(w_ockk, n_tile, n_tiles):
+    """[Cout][kh][kw][Cin] float32 -> (hi, lo) float16 matrices (n_tiles*n_tile, taps*cchunks*64):
+    K index = (tap*cchunks + chunk)*64 + ci_in_chunk, zero padded in both dimensions."""
+    cout, kh, kw, cin = w_ockk.shape
+    cch = -(-cin // TC_BK)
+    rows = n_tile * n_tiles
+    m = np.zeros((rows, kh * kw, cch * TC_BK), np.float32)
+    m[:cout, :, :cin] = w_ockk.reshape(cout, kh * kw, cin)
+    m = m.reshape(rows, kh * kw * cch * TC_BK)
+    return split_fp16(m)

@@ -1,0 +1,64 @@
+"""Unit tests of the tcgen05 convolution kernel (csrc/conv_tc.cu) through skps_debug_conv_tc,
+against torch.nn.functional.conv2d in float32 on the CPU.  Shapes are the landmark network's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_split=False, seed=0):
+    import torch
+    import torch.nn.functional as F
+    from peppa_pig_face_landmark_b200 import plan as P, runtime as rt
+    lib = rt.load_library()
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32) * 2
+    w = (rng.standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32) if with_bias else None
+    res = rng.standard_normal((N, H, W, Cout)).astype(np.float32) if with_res else None
+    n_tile, n_tiles = P.tc_tiling(Cout)
+    hi, lo = P.pack_tc_weights(w, n_tile, n_tiles)
+    hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
+    out = np.empty((N, H, W, Cout), np.float32)
+    rt.check(lib.skps_debug_conv_tc(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data,
+                                    b.ctypes.data if b is not None else None, Cout, k, dil, act, n_tile, n_tiles,
+                                    res.ctypes.data if res is not None else None, 1 if out_split else 0,
+                                    out.ctypes.data))
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    wt = torch.from_numpy(w).permute(0, 3, 1, 2).contiguous()
+    y = F.conv2d(xt, wt, torch.from_numpy(b) if b is not None else None, padding=dil * (k - 1) // 2, dilation=dil)
+    if act == 1:
+        y = torch.relu(y)
+    elif act == 2:
+        y = y * torch.clamp(y * np.float32(1 / 6) + 0.5, 0, 1)
+    y = y.permute(0, 2, 3, 1).numpy()
+    if res is not None:
+        y = y + res
+    err = np.abs(out - y).max() / (np.abs(y).max() + 1e-9)
+    return err
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout, k, dil, act
+    (2, 64, 64, 128, 128, 3, 1, 1),      # decoder/upsampler2/conv2: 40.7 % of the MACs
+    (2, 64, 64, 128, 294, 1, 1, 0),      # hm head (two N tiles, ragged Cout)
+    (2, 64, 64, 280, 128, 1, 1, 1),      # K not a multiple of 64
+    (3, 32, 32, 296, 256, 1, 1, 1),
+    (4, 16, 16, 160, 64, 3, 2, 0),       # ASPP dilated 3x3
+    (4, 16, 16, 160, 64, 3, 4, 0),
+    (2, 16, 16, 160, 960, 1, 1, 2),      # four N tiles, h-swish
+    (2, 16, 16, 960, 160, 1, 1, 0),
+    (1, 128, 128, 16, 64, 1, 1, 1),      # W = 128: one image row per tile, tiny K
+    (2, 64, 64, 24, 72, 1, 1, 1),
+    (2, 32, 32, 40, 120, 1, 1, 1),
+    (5, 32, 32, 120, 40, 1, 1, 0),
+])
+def test_conv_tc_matches_fp32(cfg):
+    err = _run(*cfg)
+    assert err < 2e-6, (cfg, err)
+
+
+def test_conv_tc_residual_and_split_output():
+    assert _run(2, 32, 32, 120, 40, 1, 1, 0, with_res=True) < 2e-6
+    assert _run(2, 64, 64, 128, 128, 3, 1, 1, out_split=True) < 2e-6
+    assert _run(2, 16, 16, 672, 112, 1, 1, 0, with_bias=False, with_res=True, out_split=True) < 2e-6
