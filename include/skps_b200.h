@@ -91,7 +91,7 @@ SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int batch, void* s
  * plan.pack_tc_weights, out float32 NHWC. */
 SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi, const void* w_lo,
                                 const float* bias, int Cout, int ksize, int dil, int act, int n_tile, int n_tiles,
-                                const float* residual, int out_split, float* out);
+                                float out_scale, const float* residual, int out_split, float* out);
 
 /* ------------------------------------------------------------------ image kernels */
 

@@ -48,7 +48,7 @@ class PlanInterp:
                 x = rd(op.ins[0])
                 if op.ins[2] is not None:
                     x = x * rd(op.ins[2])
-                w = torch.from_numpy(op.w).permute(0, 3, 1, 2).contiguous()
+                w = torch.from_numpy(getattr(op, 'w_ref', op.w)).permute(0, 3, 1, 2).contiguous()
                 y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b) if op.b is not None else None,
                              stride=op.s, padding=tuple(op.p), dilation=op.d)
                 y = _act(y, op.act).permute(0, 2, 3, 1)
@@ -85,6 +85,8 @@ class PlanInterp:
             elif t == P.OP_SCSE:
                 x = rd(op.ins[0])
                 wr(op.outs[0], x * rd(op.ins[1]) + x * rd(op.ins[2]))
+            elif t == P.OP_SCALE_CH:
+                wr(op.outs[0], rd(op.ins[0]) * rd(op.ins[1]))
             elif t == P.OP_DET_DECODE:
                 wr(op.outs[0], self._det_decode(op, [rd(v) for v in op.ins], N))
             elif t == P.OP_HM_DECODE:

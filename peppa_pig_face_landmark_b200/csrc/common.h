@@ -10,11 +10,12 @@ namespace skps {
 // ---- op codes / activations: keep in sync with peppa_pig_face_landmark_b200/plan.py ----
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
-    OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11
+    OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
+    OP_SCALE_CH = 12
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
-enum { FLAG_IN_U8 = 1 };
+enum { FLAG_IN_U8 = 1, FLAG_TC = 2 };
 enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
 
 struct View {            // 6 words
@@ -40,6 +41,8 @@ struct TView {
     int ld;            // channels of the underlying buffer (row pitch in elements per pixel)
     int c_off, c_stride, C, H, W;
     long long sample;  // elements per sample = H*W*ld
+    int fmt;           // DT_F32 / DT_U8 / DT_SPLIT16
+    long long plane;   // SPLIT16: element offset from the hi plane to the lo plane (= max_batch*sample)
 };
 
 void set_error(const char* fmt, ...);
@@ -83,6 +86,56 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+// ---- format-generic element access: float32, or float16 hi/lo planes (v = hi + lo) ------------------
+}  // namespace skps
+#include <cuda_fp16.h>
+namespace skps {
+__device__ __forceinline__ float ld1(const void* base, int fmt, long long plane, long long i) {
+    if (fmt == DT_SPLIT16) {
+        const __half* h = (const __half*)base;
+        return __half2float(h[i]) + __half2float(h[i + plane]);
+    }
+    return ((const float*)base)[i];
+}
+__device__ __forceinline__ void st1(void* base, int fmt, long long plane, long long i, float v) {
+    if (fmt == DT_SPLIT16) {
+        __half* h = (__half*)base;
+        __half hi = __float2half_rn(v);
+        h[i] = hi;
+        h[i + plane] = __float2half_rn(v - __half2float(hi));
+    } else {
+        ((float*)base)[i] = v;
+    }
+}
+// 4 consecutive elements, i a multiple of 4
+__device__ __forceinline__ float4 ld4(const void* base, int fmt, long long plane, long long i) {
+    if (fmt == DT_SPLIT16) {
+        const __half* h = (const __half*)base;
+        uint2 a = *reinterpret_cast<const uint2*>(h + i), b = *reinterpret_cast<const uint2*>(h + i + plane);
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+        float2 a01 = __half22float2(a2[0]), a23 = __half22float2(a2[1]);
+        float2 b01 = __half22float2(b2[0]), b23 = __half22float2(b2[1]);
+        return make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+    }
+    return *reinterpret_cast<const float4*>((const float*)base + i);
+}
+__device__ __forceinline__ void st4(void* base, int fmt, long long plane, long long i, float4 v) {
+    if (fmt == DT_SPLIT16) {
+        __half* h = (__half*)base;
+        __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+        float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+        uint2 a, b;
+        a.x = *reinterpret_cast<uint32_t*>(&h01); a.y = *reinterpret_cast<uint32_t*>(&h23);
+        b.x = *reinterpret_cast<uint32_t*>(&l01); b.y = *reinterpret_cast<uint32_t*>(&l23);
+        *reinterpret_cast<uint2*>(h + i) = a;
+        *reinterpret_cast<uint2*>(h + i + plane) = b;
+    } else {
+        *reinterpret_cast<float4*>((float*)base + i) = v;
+    }
+}
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 struct ConvArgs {
     TView in, out, res, gate;     // res.base / gate.base may be null
@@ -109,6 +162,7 @@ int launch_affine_act(const TView& in, const TView& out, const float* sc, const 
                       cudaStream_t s);
 int launch_scse(const TView& x, const TView& cse, const TView& sse, const TView& out, int batch, cudaStream_t s);
 int launch_det_decode(const TView* heads, const float* consts, const TView& out, int rows, int batch, cudaStream_t s);
+int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int batch, cudaStream_t s);
 int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s);
 
 }  // namespace skps

@@ -14,9 +14,9 @@ namespace skps {
 constexpr int BK = 16;
 
 struct ConvK {
-    const void* in; int in_ld, in_coff; int H, W, Cin;
-    float* out; int out_ld, out_coff, out_cstride; int Ho, Wo, Cout;
-    const float* res; int res_ld, res_coff;
+    const void* in; int in_ld, in_coff; int H, W, Cin; int in_fmt; long long in_plane;
+    void* out; int out_ld, out_coff, out_cstride; int Ho, Wo, Cout; int out_fmt; long long out_plane;
+    const void* res; int res_ld, res_coff; int res_fmt; long long res_plane;
     const float* gate; int gate_ld, gate_coff;     // per-sample (n, ci) input scale
     const float* w; const float* bias;
     int kh, kw, sh, sw, ph, pw, dh, dw, act;
@@ -92,14 +92,14 @@ conv_igemm_kernel(const ConvK p) {
                     if (ci + 2 < p.Cin) v.z = __fdiv_rn((float)src[2], 255.f);
                     if (ci + 3 < p.Cin) v.w = __fdiv_rn((float)src[3], 255.f);
                 } else {
-                    const float* src = (const float*)p.in + pix * p.in_ld + p.in_coff + ci;
+                    const long long e = pix * p.in_ld + p.in_coff + ci;
                     if (VEC) {
-                        v = *reinterpret_cast<const float4*>(src);
+                        v = ld4(p.in, p.in_fmt, p.in_plane, e);
                     } else {
-                        v.x = src[0];
-                        if (ci + 1 < p.Cin) v.y = src[1];
-                        if (ci + 2 < p.Cin) v.z = src[2];
-                        if (ci + 3 < p.Cin) v.w = src[3];
+                        v.x = ld1(p.in, p.in_fmt, p.in_plane, e);
+                        if (ci + 1 < p.Cin) v.y = ld1(p.in, p.in_fmt, p.in_plane, e + 1);
+                        if (ci + 2 < p.Cin) v.z = ld1(p.in, p.in_fmt, p.in_plane, e + 2);
+                        if (ci + 3 < p.Cin) v.w = ld1(p.in, p.in_fmt, p.in_plane, e + 3);
                     }
                     if (p.gate) {
                         const float* g = p.gate + (long long)a_n[it] * p.gate_ld + p.gate_coff + ci;
@@ -180,8 +180,8 @@ conv_igemm_kernel(const ConvK p) {
     for (int i = 0; i < TM; ++i) {
         int m = m0 + ty * TM + i;
         if (m >= p.M) continue;
-        float* orow = p.out + (long long)m * p.out_ld + p.out_coff;
-        const float* rrow = p.res ? p.res + (long long)m * p.res_ld + p.res_coff : nullptr;
+        const long long obase = (long long)m * p.out_ld + p.out_coff;
+        const long long rbase = (long long)m * p.res_ld + p.res_coff;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             int co = n0 + tx * TN + j;
@@ -189,8 +189,8 @@ conv_igemm_kernel(const ConvK p) {
             float v = acc[i][j];
             if (p.bias) v += p.bias[co];
             v = apply_act(v, p.act);
-            if (rrow) v += rrow[co];
-            orow[(long long)co * p.out_cstride] = v;
+            if (p.res) v += ld1(p.res, p.res_fmt, p.res_plane, rbase + co);
+            st1(p.out, p.out_fmt, p.out_plane, obase + (long long)co * p.out_cstride, v);
         }
     }
 }
@@ -209,9 +209,10 @@ static int launch_cfg(const ConvK& k, bool vec, bool in_u8, cudaStream_t s) {
 int launch_conv(const ConvArgs& a, cudaStream_t s) {
     ConvK k;
     k.in = a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.H = a.in.H; k.W = a.in.W; k.Cin = a.in.C;
-    k.out = (float*)a.out.base; k.out_ld = a.out.ld; k.out_coff = a.out.c_off; k.out_cstride = a.out.c_stride;
-    k.Ho = a.out.H; k.Wo = a.out.W; k.Cout = a.out.C;
-    k.res = (const float*)a.res.base; k.res_ld = a.res.ld; k.res_coff = a.res.c_off;
+    k.in_fmt = a.in.fmt; k.in_plane = a.in.plane;
+    k.out = a.out.base; k.out_ld = a.out.ld; k.out_coff = a.out.c_off; k.out_cstride = a.out.c_stride;
+    k.Ho = a.out.H; k.Wo = a.out.W; k.Cout = a.out.C; k.out_fmt = a.out.fmt; k.out_plane = a.out.plane;
+    k.res = a.res.base; k.res_ld = a.res.ld; k.res_coff = a.res.c_off; k.res_fmt = a.res.fmt; k.res_plane = a.res.plane;
     k.gate = (const float*)a.gate.base; k.gate_ld = a.gate.ld; k.gate_coff = a.gate.c_off;
     k.w = a.w; k.bias = a.bias;
     k.kh = a.kh; k.kw = a.kw; k.sh = a.sh; k.sw = a.sw; k.ph = a.ph; k.pw = a.pw; k.dh = a.dh; k.dw = a.dw;

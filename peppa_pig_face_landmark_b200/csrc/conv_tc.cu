@@ -242,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 for (int j = 0; j < 32; ++j) {
                     if (j < nvalid) {
                         float b = p.bias ? __ldg(p.bias + co0 + j) : 0.f;
-                        v[j] = apply_act(v[j] + b, p.act);
+                        v[j] = apply_act(v[j] * p.out_scale + b, p.act);
                     }
                 }
                 if (p.res) {
@@ -356,10 +356,10 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.tiles_per_img = (s.H / k.bh) * (s.W / k.bw);
     k.taps = s.kh * s.kw; k.kw = s.kw; k.dil = s.dil; k.pad = s.pad;
     k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;
-    k.Cout = s.Cout; k.act = s.act;
+    k.Cout = s.Cout; k.act = s.act; k.out_scale = s.out_scale;
     k.n_tile = s.n_tile; k.n_tiles = s.n_tiles;
     const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
-    int stages = (int)((227 * 1024 - 2048) / stage_bytes);
+    int stages = (int)((227 * 1024 - 1024 - 1024) / stage_bytes);   // minus static smem slack and alignment pad
     k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
     L.smem_bytes = (int)(k.stages * stage_bytes + 1024);
@@ -395,7 +395,7 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.res = s.res; k.res_fmt = s.res_fmt; k.res_plane = s.res_plane; k.res_ld = s.res_ld; k.res_coff = s.res_coff;
     static bool attr_set = false;
     if (!attr_set) {
-        SKPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SKPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
         attr_set = true;
     }
     return 0;
@@ -432,8 +432,8 @@ using namespace skps;
 //   out    [host] float32 NHWC (N,H,W,Cout)
 extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi,
                                            const void* w_lo, const float* bias, int Cout, int ksize, int dil, int act,
-                                           int n_tile, int n_tiles, const float* residual, int out_split,
-                                           float* out) {
+                                           int n_tile, int n_tiles, float out_scale, const float* residual,
+                                           int out_split, float* out) {
     SKPS_CHECK(x && w_hi && w_lo && out, "debug_conv_tc: null argument");
     const long long nin = (long long)N * H * W * Cin, nout = (long long)N * H * W * Cout;
     const int cchunks = (Cin + TC_BK - 1) / TC_BK;
@@ -463,7 +463,7 @@ extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, 
     s.H = H; s.W = W; s.Cin = Cin; s.in_ld = Cin; s.in_coff = 0; s.max_batch = N;
     s.in_base = d_split; s.in_plane = nin;
     s.kh = s.kw = ksize; s.dil = dil; s.pad = dil * (ksize - 1) / 2;
-    s.Cout = Cout; s.act = act; s.n_tile = n_tile; s.n_tiles = n_tiles;
+    s.Cout = Cout; s.act = act; s.n_tile = n_tile; s.n_tiles = n_tiles; s.out_scale = out_scale;
     s.w_hi = d_wh; s.w_lo = d_wl; s.bias = d_bias;
     s.out = out_split ? (void*)d_osplit : (void*)d_out; s.out_fmt = out_split ? DT_SPLIT16 : DT_F32;
     s.out_plane = nout; s.out_ld = Cout; s.out_coff = 0; s.out_cstride = 1;

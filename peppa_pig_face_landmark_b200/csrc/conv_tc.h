@@ -10,6 +10,7 @@ struct TcK {                     // kernel parameters
     int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
     int taps, kw, dil, pad, cchunks;
     int Cout, act, stages;
+    float out_scale;             // exact power of two undoing the weight pre-scale
     const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
     const void* res; int res_fmt; long long res_plane; int res_ld, res_coff;
@@ -26,6 +27,7 @@ struct TcSetup {
     const void* in_base; long long in_plane;      // hi plane base (fp16), lo plane = base + in_plane elements
     int kh, kw, dil, pad;
     int Cout, act, n_tile, n_tiles;
+    float out_scale;
     const void* w_hi; const void* w_lo;           // device, (n_tiles*n_tile, K_pad) fp16
     const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;

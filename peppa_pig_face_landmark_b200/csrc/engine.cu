@@ -11,6 +11,7 @@
 
 #include "../../include/skps_b200.h"
 #include "common.h"
+#include "conv_tc.h"
 
 namespace skps {
 
@@ -43,10 +44,22 @@ struct skps_engine {
     std::map<int, cudaGraphExec_t> graphs;   // batch -> captured forward
     int launches = 0;
     bool use_graph = true;
+    int num_sms = 148;
+    std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
 };
 
 static size_t buf_elems(const BufDesc& b) { return (size_t)b.C * b.H * b.W; }
-static size_t buf_bytes(const BufDesc& b) { return buf_elems(b) * (b.dtype == DT_U8 ? 1 : 4); }
+static size_t buf_bytes(const BufDesc& b) { return buf_elems(b) * (b.dtype == DT_U8 ? 1 : 4); }   // SPLIT16 = 2+2 bytes
+
+static float half_bits_to_float(uint16_t h) {
+    uint32_t sign = (uint32_t)(h >> 15) << 31, exp = (h >> 10) & 31, man = h & 1023, bits;
+    if (exp == 0) {
+        if (man == 0) { bits = sign; }
+        else { int e2 = -1; do { ++e2; man <<= 1; } while (!(man & 1024)); bits = sign | ((uint32_t)(112 - e2) << 23) | ((man & 1023) << 13); }
+    } else if (exp == 31) { bits = sign | 0x7F800000u | (man << 13); }
+    else { bits = sign | ((exp + 112) << 23) | (man << 13); }
+    float f; memcpy(&f, &bits, 4); return f;
+}
 
 static TView resolve(const skps_engine* e, const View& v) {
     TView t;
@@ -57,6 +70,8 @@ static TView resolve(const skps_engine* e, const View& v) {
     t.ld = b.C;
     t.c_off = v.c_off; t.c_stride = v.c_stride; t.C = v.C; t.H = b.H; t.W = b.W;
     t.sample = (long long)b.C * b.H * b.W;
+    t.fmt = b.dtype;
+    t.plane = t.sample * e->max_batch;
     return t;
 }
 
@@ -71,6 +86,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
         int rc = 0;
         switch (op.type) {
             case OP_CONV: {
+                if (op.flags & FLAG_TC) {
+                    rc = tc_launch(e->tc[i], batch, e->num_sms, s);
+                    break;
+                }
                 ConvArgs a;
                 a.in = in0; a.res = in1; a.gate = in2; a.out = out0; a.w = w; a.bias = b;
                 a.kh = op.kh; a.kw = op.kw; a.sh = op.sh; a.sw = op.sw; a.ph = op.ph; a.pw = op.pw;
@@ -94,6 +113,7 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_GAP: rc = launch_gap(in0, out0, batch, s); break;
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
+            case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
             case OP_DET_DECODE: {
                 TView heads[3] = {in0, in1, in2};
                 rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);
@@ -160,6 +180,34 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         set_error("cudaMalloc staging");
         return fail("alloc");
     }
+    cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
+    // tensor-core conv layers: TMA descriptors over the (fixed) activation buffers and weight matrices
+    e->tc.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const OpDesc& op = e->ops[i];
+        if (op.type != OP_CONV || !(op.flags & FLAG_TC)) continue;
+        TView in0 = resolve(e, op.in[0]), res = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
+        if (in0.fmt != DT_SPLIT16 || in0.c_stride != 1 || op.in[2].buf >= 0 || op.sh != 1 || op.sw != 1) {
+            set_error("op %d: tensor-core conv needs a SPLIT16 unit-stride input and no gate", i);
+            return fail("tc");
+        }
+        TcSetup s = {};
+        s.H = in0.H; s.W = in0.W; s.Cin = in0.C; s.in_ld = in0.ld; s.in_coff = in0.c_off; s.max_batch = max_batch;
+        s.in_base = in0.base; s.in_plane = in0.plane;
+        s.kh = op.kh; s.kw = op.kw; s.dil = op.dh; s.pad = op.ph;
+        s.Cout = out0.C; s.act = op.act; s.n_tile = op.i[0]; s.n_tiles = op.i[1]; s.out_scale = op.f[0];
+        s.w_hi = e->d_weights + op.w_off; s.w_lo = e->d_weights + op.i[2];
+        s.bias = op.b_off >= 0 ? e->d_weights + op.b_off : nullptr;
+        s.out = out0.base; s.out_fmt = out0.fmt; s.out_plane = out0.plane; s.out_ld = out0.ld; s.out_coff = out0.c_off;
+        s.out_cstride = out0.c_stride;
+        s.res = res.base; s.res_fmt = res.fmt; s.res_plane = res.plane; s.res_ld = res.ld; s.res_coff = res.c_off;
+        if (op.dh != op.dw || op.ph != op.pw || tc_prepare(e->tc[i], s)) {
+            char tmp[900];
+            snprintf(tmp, sizeof(tmp), "%s", get_error());
+            set_error("op %d: %s", i, tmp);
+            return fail("tc");
+        }
+    }
     *out = e;
     return 0;
 }
@@ -207,7 +255,18 @@ extern "C" SKPS_API int skps_engine_read_buffer(skps_engine* e, int buf, int bat
     SKPS_CHECK(e && buf >= 0 && buf < (int)e->bufs.size() && batch <= e->max_batch, "read_buffer: bad arguments");
     SKPS_CUDA(cudaSetDevice(e->device));
     SKPS_CUDA(cudaDeviceSynchronize());
-    SKPS_CUDA(cudaMemcpy(dst, e->dbuf[buf], buf_bytes(e->bufs[buf]) * batch, cudaMemcpyDeviceToHost));
+    const BufDesc& b = e->bufs[buf];
+    if (b.dtype == DT_SPLIT16) {
+        // hi plane + lo plane (each max_batch samples) -> float32
+        size_t n = buf_elems(b) * (size_t)batch, plane = buf_elems(b) * (size_t)e->max_batch;
+        std::vector<uint16_t> hi(n), lo(n);
+        SKPS_CUDA(cudaMemcpy(hi.data(), e->dbuf[buf], n * 2, cudaMemcpyDeviceToHost));
+        SKPS_CUDA(cudaMemcpy(lo.data(), (const uint16_t*)e->dbuf[buf] + plane, n * 2, cudaMemcpyDeviceToHost));
+        float* d = (float*)dst;
+        for (size_t i = 0; i < n; ++i) d[i] = half_bits_to_float(hi[i]) + half_bits_to_float(lo[i]);
+        return 0;
+    }
+    SKPS_CUDA(cudaMemcpy(dst, e->dbuf[buf], buf_bytes(b) * batch, cudaMemcpyDeviceToHost));
     return 0;
 }
 extern "C" SKPS_API int skps_engine_launches_per_forward(const skps_engine* e) { return e ? e->launches : 0; }

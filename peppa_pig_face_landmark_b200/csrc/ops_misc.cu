@@ -17,8 +17,8 @@ static inline int blocks_for(long long n, int threads) {
 // (kps_student.onnx conv_dw nodes, e.g. node 4; yolov5n-0.5.onnx branch*.0/.3 nodes.)
 // ------------------------------------------------------------------------------------------
 struct DwK {
-    const float* in; int in_ld, in_coff, H, W;
-    float* out; int out_ld, out_coff, out_cstride, Ho, Wo, C;
+    const void* in; int in_ld, in_coff, H, W; int in_fmt; long long in_plane;
+    void* out; int out_ld, out_coff, out_cstride, Ho, Wo, C; int out_fmt; long long out_plane;
     const float* w; const float* bias;
     int kh, kw, sh, sw, ph, pw, dh, dw, act;
     long long total;   // batch*Ho*Wo*(C/4)
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
         for (int kx = 0; kx < p.kw; ++kx) {
             int ix = ix0 + kx * p.dw;
             if (ix < 0 || ix >= p.W) continue;
-            const float4 v = *reinterpret_cast<const float4*>(
-                p.in + (((long long)n * p.H + iy) * p.W + ix) * p.in_ld + p.in_coff + c);
+            const float4 v = ld4(p.in, p.in_fmt, p.in_plane,
+                                  (((long long)n * p.H + iy) * p.W + ix) * p.in_ld + p.in_coff + c);
             const float4 w = *reinterpret_cast<const float4*>(p.w + (ky * p.kw + kx) * p.C + c);
             acc.x = fmaf(v.x, w.x, acc.x);
             acc.y = fmaf(v.y, w.y, acc.y);
@@ -55,22 +55,23 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
     acc.y = apply_act(acc.y, p.act);
     acc.z = apply_act(acc.z, p.act);
     acc.w = apply_act(acc.w, p.act);
-    float* o = p.out + pix * p.out_ld + p.out_coff;
+    const long long o = pix * p.out_ld + p.out_coff;
     if (p.out_cstride == 1) {
-        *reinterpret_cast<float4*>(o + c) = acc;
+        st4(p.out, p.out_fmt, p.out_plane, o + c, acc);
     } else {
-        o[(long long)(c + 0) * p.out_cstride] = acc.x;
-        o[(long long)(c + 1) * p.out_cstride] = acc.y;
-        o[(long long)(c + 2) * p.out_cstride] = acc.z;
-        o[(long long)(c + 3) * p.out_cstride] = acc.w;
+        st1(p.out, p.out_fmt, p.out_plane, o + (long long)(c + 0) * p.out_cstride, acc.x);
+        st1(p.out, p.out_fmt, p.out_plane, o + (long long)(c + 1) * p.out_cstride, acc.y);
+        st1(p.out, p.out_fmt, p.out_plane, o + (long long)(c + 2) * p.out_cstride, acc.z);
+        st1(p.out, p.out_fmt, p.out_plane, o + (long long)(c + 3) * p.out_cstride, acc.w);
     }
 }
 
 int launch_dwconv(const DwArgs& a, cudaStream_t s) {
     DwK k;
-    k.in = (const float*)a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.H = a.in.H; k.W = a.in.W;
-    k.out = (float*)a.out.base; k.out_ld = a.out.ld; k.out_coff = a.out.c_off; k.out_cstride = a.out.c_stride;
-    k.Ho = a.out.H; k.Wo = a.out.W; k.C = a.out.C;
+    k.in = a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.H = a.in.H; k.W = a.in.W;
+    k.in_fmt = a.in.fmt; k.in_plane = a.in.plane;
+    k.out = a.out.base; k.out_ld = a.out.ld; k.out_coff = a.out.c_off; k.out_cstride = a.out.c_stride;
+    k.Ho = a.out.H; k.Wo = a.out.W; k.C = a.out.C; k.out_fmt = a.out.fmt; k.out_plane = a.out.plane;
     k.w = a.w; k.bias = a.bias;
     k.kh = a.kh; k.kw = a.kw; k.sh = a.sh; k.sw = a.sw; k.ph = a.ph; k.pw = a.pw; k.dh = a.dh; k.dw = a.dw;
     k.act = a.act;
@@ -87,15 +88,16 @@ int launch_dwconv(const DwArgs& a, cudaStream_t s) {
 // Generic per-element kernels over (n, y, x, c) of the OUTPUT view.
 // ------------------------------------------------------------------------------------------
 struct EwK {
-    const float* in; int in_ld, in_coff, in_cs, H, W;
-    float* out; int out_ld, out_coff, out_cs, Ho, Wo, C;
-    const float* a; const float* b;     // op specific
-    int a_ld, a_coff, b_ld, b_coff;
+    const void* in; int in_ld, in_coff, in_cs, H, W; int in_fmt; long long in_plane;
+    void* out; int out_ld, out_coff, out_cs, Ho, Wo, C; int out_fmt; long long out_plane;
+    const void* a; const void* b;     // op specific
+    int a_ld, a_coff, b_ld, b_coff; int a_fmt, b_fmt; long long a_plane, b_plane;
     int act;
     long long total;
 };
 
-template <int MODE>   // 0 maxpool2 ceil, 1 nearest, 2 bilinear2x, 3 copy, 4 affine+act, 5 scse
+#define SRC(off) ld1(p.in, p.in_fmt, p.in_plane, sbase + (off))
+template <int MODE>   // 0 maxpool2 ceil, 1 nearest, 2 bilinear2x, 3 copy, 4 affine+act, 5 scse, 6 scale by gate[n,c]
 __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.total) return;
@@ -105,21 +107,21 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
     long long t = pix / p.Wo;
     int oy = (int)(t % p.Ho);
     int n = (int)(t / p.Ho);
-    const float* src = p.in + (long long)n * p.H * p.W * p.in_ld + p.in_coff + (long long)c * p.in_cs;
+    const long long sbase = (long long)n * p.H * p.W * p.in_ld + p.in_coff + (long long)c * p.in_cs;
     float v;
     if (MODE == 0) {
         // MaxPool 2x2 stride 2, ceil_mode=1, no padding (yolov5n-0.5.onnx node 9)
         int y0 = oy * 2, x0 = ox * 2;
-        v = src[((long long)y0 * p.W + x0) * p.in_ld];
-        if (x0 + 1 < p.W) v = fmaxf(v, src[((long long)y0 * p.W + x0 + 1) * p.in_ld]);
+        v = SRC(((long long)y0 * p.W + x0) * p.in_ld);
+        if (x0 + 1 < p.W) v = fmaxf(v, SRC(((long long)y0 * p.W + x0 + 1) * p.in_ld));
         if (y0 + 1 < p.H) {
-            v = fmaxf(v, src[((long long)(y0 + 1) * p.W + x0) * p.in_ld]);
-            if (x0 + 1 < p.W) v = fmaxf(v, src[((long long)(y0 + 1) * p.W + x0 + 1) * p.in_ld]);
+            v = fmaxf(v, SRC(((long long)(y0 + 1) * p.W + x0) * p.in_ld));
+            if (x0 + 1 < p.W) v = fmaxf(v, SRC(((long long)(y0 + 1) * p.W + x0 + 1) * p.in_ld));
         }
     } else if (MODE == 1) {
         // Resize nearest, asymmetric, floor: src = floor(dst * in / out)
         int iy = (int)(((long long)oy * p.H) / p.Ho), ix = (int)(((long long)ox * p.W) / p.Wo);
-        v = src[((long long)iy * p.W + ix) * p.in_ld];
+        v = SRC(((long long)iy * p.W + ix) * p.in_ld);
     } else if (MODE == 2) {
         // Resize linear, half_pixel, scale 2 (kps_student.onnx nodes 176, 193)
         float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
@@ -127,28 +129,34 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
         int y1 = min(y0 + 1, p.H - 1), x1 = min(x0 + 1, p.W - 1);
         float ly = sy - y0, lx = sx - x0;
         float hy = 1.f - ly, hx = 1.f - lx;
-        float p00 = src[((long long)y0 * p.W + x0) * p.in_ld], p01 = src[((long long)y0 * p.W + x1) * p.in_ld];
-        float p10 = src[((long long)y1 * p.W + x0) * p.in_ld], p11 = src[((long long)y1 * p.W + x1) * p.in_ld];
+        float p00 = SRC(((long long)y0 * p.W + x0) * p.in_ld), p01 = SRC(((long long)y0 * p.W + x1) * p.in_ld);
+        float p10 = SRC(((long long)y1 * p.W + x0) * p.in_ld), p11 = SRC(((long long)y1 * p.W + x1) * p.in_ld);
         v = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
     } else {
-        v = src[((long long)oy * p.W + ox) * p.in_ld];
+        v = SRC(((long long)oy * p.W + ox) * p.in_ld);
         if (MODE == 4) {
-            v = apply_act(fmaf(v, p.a[c], p.b[c]), p.act);
+            v = apply_act(fmaf(v, ((const float*)p.a)[c], ((const float*)p.b)[c]), p.act);
         } else if (MODE == 5) {
             // scSE (model.py:117-130): x*cSE[n,c] + x*sSE[n,h,w]
-            float cs = p.a[(long long)n * p.a_ld + p.a_coff + c];
-            float ss = p.b[((long long)n * p.H * p.W + (long long)oy * p.W + ox) * p.b_ld + p.b_coff];
+            float cs = ld1(p.a, p.a_fmt, p.a_plane, (long long)n * p.a_ld + p.a_coff + c);
+            float ss = ld1(p.b, p.b_fmt, p.b_plane,
+                           ((long long)n * p.H * p.W + (long long)oy * p.W + ox) * p.b_ld + p.b_coff);
             v = __fadd_rn(__fmul_rn(v, cs), __fmul_rn(v, ss));
+        } else if (MODE == 6) {
+            // squeeze-excite gate applied ahead of a tensor-core conv: x * gate[n,c]
+            v = v * ld1(p.a, p.a_fmt, p.a_plane, (long long)n * p.a_ld + p.a_coff + c);
         }
     }
-    p.out[pix * p.out_ld + p.out_coff + (long long)c * p.out_cs] = v;
+    st1(p.out, p.out_fmt, p.out_plane, pix * p.out_ld + p.out_coff + (long long)c * p.out_cs, v);
 }
+#undef SRC
 
 static EwK make_ew(const TView& in, const TView& out, int batch) {
     EwK k = {};
-    k.in = (const float*)in.base; k.in_ld = in.ld; k.in_coff = in.c_off; k.in_cs = in.c_stride; k.H = in.H; k.W = in.W;
-    k.out = (float*)out.base; k.out_ld = out.ld; k.out_coff = out.c_off; k.out_cs = out.c_stride;
-    k.Ho = out.H; k.Wo = out.W; k.C = out.C;
+    k.in = in.base; k.in_ld = in.ld; k.in_coff = in.c_off; k.in_cs = in.c_stride; k.H = in.H; k.W = in.W;
+    k.in_fmt = in.fmt; k.in_plane = in.plane;
+    k.out = out.base; k.out_ld = out.ld; k.out_coff = out.c_off; k.out_cs = out.c_stride;
+    k.Ho = out.H; k.Wo = out.W; k.C = out.C; k.out_fmt = out.fmt; k.out_plane = out.plane;
     k.total = (long long)batch * out.H * out.W * out.C;
     return k;
 }
@@ -188,24 +196,30 @@ int launch_affine_act(const TView& in, const TView& out, const float* sc, const 
 int launch_scse(const TView& x, const TView& cse, const TView& sse, const TView& out, int batch, cudaStream_t s) {
     SKPS_CHECK(x.C == out.C && cse.C == x.C && sse.C == 1 && sse.H == x.H && sse.W == x.W, "scse: shape");
     EwK k = make_ew(x, out, batch);
-    k.a = (const float*)cse.base; k.a_ld = cse.ld; k.a_coff = cse.c_off;
-    k.b = (const float*)sse.base; k.b_ld = sse.ld; k.b_coff = sse.c_off;
+    k.a = cse.base; k.a_ld = cse.ld; k.a_coff = cse.c_off; k.a_fmt = cse.fmt; k.a_plane = cse.plane;
+    k.b = sse.base; k.b_ld = sse.ld; k.b_coff = sse.c_off; k.b_fmt = sse.fmt; k.b_plane = sse.plane;
     LAUNCH_EW(5, k, s)
+}
+int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int batch, cudaStream_t s) {
+    SKPS_CHECK(x.C == out.C && gate.C == x.C && x.H == out.H && x.W == out.W, "scale_ch: shape");
+    EwK k = make_ew(x, out, batch);
+    k.a = gate.base; k.a_ld = gate.ld; k.a_coff = gate.c_off; k.a_fmt = gate.fmt; k.a_plane = gate.plane;
+    LAUNCH_EW(6, k, s)
 }
 
 // ------------------------------------------------------------------------------------------
 // Global average pool: (N,H,W,C) -> (N,1,1,C).  Block = 32 channels x 8 pixel lanes, fixed
 // summation order (deterministic).  ReduceMean(2,3) / GlobalAveragePool nodes.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gap_kernel(const float* in, int in_ld, int in_coff, int HW, int C,
-                                                  float* out, int out_ld, int out_coff) {
+__global__ void __launch_bounds__(256) gap_kernel(const void* in, int in_fmt, long long in_plane, int in_ld, int in_coff,
+                                                  int HW, int C, float* out, int out_ld, int out_coff) {
     __shared__ float part[8][33];
     int n = blockIdx.y;
     int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
     if (c < C) {
-        const float* src = in + (long long)n * HW * in_ld + in_coff + c;
-        for (int p = threadIdx.y; p < HW; p += 8) s += src[(long long)p * in_ld];
+        const long long sb = (long long)n * HW * in_ld + in_coff + c;
+        for (int p = threadIdx.y; p < HW; p += 8) s += ld1(in, in_fmt, in_plane, sb + (long long)p * in_ld);
     }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
@@ -220,7 +234,8 @@ __global__ void __launch_bounds__(256) gap_kernel(const float* in, int in_ld, in
 int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s) {
     SKPS_CHECK(in.C == out.C && out.H == 1 && out.W == 1 && in.c_stride == 1 && out.c_stride == 1, "gap: shape");
     dim3 grid((in.C + 31) / 32, batch), block(32, 8);
-    gap_kernel<<<grid, block, 0, s>>>((const float*)in.base, in.ld, in.c_off, in.H * in.W, in.C,
+    SKPS_CHECK(out.fmt == DT_F32, "gap: output must be float32");
+    gap_kernel<<<grid, block, 0, s>>>(in.base, in.fmt, in.plane, in.ld, in.c_off, in.H * in.W, in.C,
                                       (float*)out.base, out.ld, out.c_off);
     SKPS_CUDA(cudaGetLastError());
     return 0;
@@ -346,7 +361,8 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
 }
 
 int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s) {
-    SKPS_CHECK(hm.C == 3 * npts && npts <= 128 && hm.c_stride == 1 && hm.H == hm.W, "hm_decode: shape");
+    SKPS_CHECK(hm.C == 3 * npts && npts <= 128 && hm.c_stride == 1 && hm.H == hm.W && hm.fmt == DT_F32,
+               "hm_decode: shape/format");
     dim3 block(128, 8);
     hm_decode_kernel<<<batch, block, 0, s>>>((const float*)hm.base, hm.ld, hm.c_off, hm.H, hm.W, npts,
                                              (float*)xy.base, xy.ld, (float*)score.base, score.ld);

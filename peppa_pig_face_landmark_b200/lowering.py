@@ -79,7 +79,8 @@ _ACT_AFTER = {"Relu": P.ACT_RELU}
 
 
 class _Lowerer:
-    def __init__(self, graph, name, in_hw, input_u8=True):
+    def __init__(self, graph, name, in_hw, input_u8=True, use_tc=True):
+        self.use_tc = use_tc
         self.g = graph
         self.plan = P.Plan(name)
         self.nodes = graph.nodes
@@ -367,6 +368,20 @@ class _Lowerer:
         if self.det_heads:
             self._emit_det_decode()
 
+    def _tc_eligible(self, xin, k, s, p, d, flags):
+        """Shapes csrc/conv_tc.cu handles: stride-1 'same' square convs whose 128-pixel tiles are whole
+        image-row blocks, channel windows aligned for TMA (16-byte rows of float16)."""
+        if not self.use_tc or (flags & P.FLAG_IN_U8) or xin.buf.dtype == P.DT_U8:
+            return False
+        if list(s) != [1, 1] or k[0] != k[1] or d[0] != d[1] or p[0] != p[1] or p[0] != d[0] * (k[0] - 1) // 2:
+            return False
+        if xin.c_stride != 1 or xin.C % 8 or xin.c_off % 8 or xin.buf.C % 8:
+            return False
+        H, W = xin.H, xin.W
+        if W >= 128:
+            return W % 128 == 0
+        return W >= 8 and 128 % W == 0 and H % (128 // W) == 0
+
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
         t = self.t[name]
@@ -399,8 +414,24 @@ class _Lowerer:
             if groups == 1:
                 wk = np.ascontiguousarray(w.transpose(0, 2, 3, 1))      # [Cout][kh][kw][Cin]
                 res = self.view(f["res"]) if f.get("res") else None
-                o = P.Op(P.OP_CONV, [xin, res, gate], [out_v], f["act"], k, s, p[:2], d, wk, b, flags,
-                         name=n.name)
+                if self._tc_eligible(xin, k, s, p, d, flags):
+                    # tcgen05 path (csrc/conv_tc.cu): float16 hi/lo operands, input buffer in SPLIT16 format
+                    if gate is not None:
+                        # squeeze-excite scale cannot ride on a TMA-fed operand: apply it in its own pass
+                        sb = pl.new_buf(xin.C, xin.H, xin.W, P.DT_SPLIT16, n.name + ":se_scaled")
+                        sv = P.View(sb, 0, 1, xin.C)
+                        pl.ops.append(P.Op(P.OP_SCALE_CH, [xin, gate], [sv], name=n.name + ":se_scale"))
+                        xin, gate = sv, None
+                    xin.buf.dtype = P.DT_SPLIT16
+                    n_tile, n_tiles = P.tc_tiling(w.shape[0])
+                    hi, lo, out_scale = P.pack_tc_weights(wk, n_tile, n_tiles)
+                    o = P.Op(P.OP_CONV, [xin, res, None], [out_v], f["act"], k, s, p[:2], d, hi, b,
+                             flags | P.FLAG_TC, ints=[n_tile, n_tiles, 0, 0], floats=[out_scale], name=n.name)
+                    o.w2 = lo
+                else:
+                    o = P.Op(P.OP_CONV, [xin, res, gate], [out_v], f["act"], k, s, p[:2], d, wk, b, flags,
+                             name=n.name)
+                o.w_ref = wk
                 pl.macs += out_t.C * out_t.H * out_t.W * w.shape[1] * k[0] * k[1]
             else:
                 assert groups == w.shape[0] and w.shape[1] == 1 and gate is None and not f.get("res")
@@ -539,10 +570,11 @@ class _Lowerer:
         return None
 
 
-def lower(onnx_path, in_hw, name=None, input_u8=True):
-    """Build the plan for one of the reference's graphs at a fixed input size."""
+def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
+    """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
+    eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
     g = load_onnx(onnx_path)
-    lw = _Lowerer(g, name or onnx_path, in_hw, input_u8)
+    lw = _Lowerer(g, name or onnx_path, in_hw, input_u8, use_tc)
     lw.analyse()
     lw.emit()
     if not lw.plan.outputs:

@@ -26,12 +26,13 @@ OP_AFFINE_ACT = 8     # per-channel x*s+t then act (explicit BatchNormalization)
 OP_SCSE = 9           # x*cse[n,c] + x*sse[n,h,w]
 OP_DET_DECODE = 10    # yolov5-face head decode -> (N,rows,16)
 OP_HM_DECODE = 11     # heat-map argmax + offset decode -> (N,196),(N,98)
+OP_SCALE_CH = 12      # x * gate[n,c]  (squeeze-excite applied ahead of a tensor-core conv)
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
 
 ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_SILU, ACT_SIGMOID, ACT_HSIGMOID = range(6)
 
-DT_F32, DT_U8 = 0, 1
+DT_F32, DT_U8, DT_SPLIT16 = 0, 1, 2     # SPLIT16: float16 hi plane + float16 lo plane, v = hi + lo
 
 OP_WORDS = 64
 VIEW_WORDS = 6
@@ -83,6 +84,7 @@ class Op:
         self.w, self.b = w, b                # numpy float32 arrays (already in kernel layout) or None
         self.flags, self.ints, self.floats, self.name = flags, list(ints), list(floats), name
         self.w_off = self.b_off = -1
+        self.w2 = None                       # FLAG_TC: lo-plane weight matrix; its blob offset goes to ints[2]
 
     def __repr__(self):
         return "%s %s -> %s act=%d k=%s s=%s d=%s %s" % (OP_NAMES[self.type], self.ins, self.outs,
@@ -90,6 +92,7 @@ class Op:
 
 
 FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
+FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo matrix (float16 bytes in the blob)
 
 
 class Plan:
@@ -122,8 +125,20 @@ class Plan:
                 parts.append(np.zeros(pad, np.float32))
             off += a.size + pad
             return start
+        def put_raw(a):
+            # float16 matrices travel as raw bytes inside the float32 blob
+            raw = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+            pad = (-raw.size) % 16
+            if pad:
+                raw = np.concatenate([raw, np.zeros(pad, np.uint8)])
+            return put(raw.view(np.float32))
         for op in self.ops:
-            op.w_off = put(op.w) if op.w is not None else -1
+            if op.flags & FLAG_TC:
+                op.w_off = put_raw(op.w)
+                lo_off = put_raw(op.w2)
+                op.ints = list(op.ints[:2]) + [lo_off] + list(op.ints[3:])
+            else:
+                op.w_off = put(op.w) if op.w is not None else -1
             op.b_off = put(op.b) if op.b is not None else -1
         return np.concatenate(parts) if parts else np.zeros(4, np.float32)
 
@@ -176,12 +191,18 @@ def split_fp16(a):
 
 
 def pack_tc_weights(w_ockk, n_tile, n_tiles):
-    """[Cout][kh][kw][Cin] float32 -> (hi, lo) float16 matrices (n_tiles*n_tile, taps*cchunks*64):
-    K index = (tap*cchunks + chunk)*64 + ci_in_chunk, zero padded in both dimensions."""
+    """[Cout][kh][kw][Cin] float32 -> (hi, lo, out_scale): float16 matrices (n_tiles*n_tile,
+    taps*cchunks*64) with K index = (tap*cchunks + chunk)*64 + ci_in_chunk, zero padded in both
+    dimensions.  The weights are pre-multiplied by an exact power of two so that the lo parts stay
+    in float16's normal range; the kernel multiplies the accumulator by out_scale = 2^-s."""
     cout, kh, kw, cin = w_ockk.shape
+    wmax = float(np.abs(w_ockk).max())
+    s_exp = int(np.floor(np.log2(8192.0 / wmax))) if wmax > 0 else 0
+    w_ockk = (w_ockk * np.float32(2.0 ** s_exp)).astype(np.float32)
     cch = -(-cin // TC_BK)
     rows = n_tile * n_tiles
     m = np.zeros((rows, kh * kw, cch * TC_BK), np.float32)
     m[:cout, :, :cin] = w_ockk.reshape(cout, kh * kw, cin)
     m = m.reshape(rows, kh * kw * cch * TC_BK)
-    return split_fp16(m)
+    hi, lo = split_fp16(m)
+    return hi, lo, float(2.0 ** (-s_exp))

@@ -45,7 +45,7 @@ SIGNATURES = {
     "skps_engine_launches_per_forward": (C.c_int, [c_vp]),
     "skps_engine_run_op": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "skps_debug_conv_tc": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int,
-                                     C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_vp, C.c_int, c_vp]),
     "skps_letterbox": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "skps_detect_post": (C.c_int, [c_vp, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -17,12 +17,12 @@ def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_sp
     b = rng.standard_normal(Cout).astype(np.float32) if with_bias else None
     res = rng.standard_normal((N, H, W, Cout)).astype(np.float32) if with_res else None
     n_tile, n_tiles = P.tc_tiling(Cout)
-    hi, lo = P.pack_tc_weights(w, n_tile, n_tiles)
+    hi, lo, out_scale = P.pack_tc_weights(w, n_tile, n_tiles)
     hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
     out = np.empty((N, H, W, Cout), np.float32)
     rt.check(lib.skps_debug_conv_tc(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data,
                                     b.ctypes.data if b is not None else None, Cout, k, dil, act, n_tile, n_tiles,
-                                    res.ctypes.data if res is not None else None, 1 if out_split else 0,
+                                    out_scale, res.ctypes.data if res is not None else None, 1 if out_split else 0,
                                     out.ctypes.data))
     xt = torch.from_numpy(x).permute(0, 3, 1, 2)
     wt = torch.from_numpy(w).permute(0, 3, 1, 2).contiguous()
@@ -55,10 +55,10 @@ def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_sp
 ])
 def test_conv_tc_matches_fp32(cfg):
     err = _run(*cfg)
-    assert err < 2e-6, (cfg, err)
+    assert err < 3e-6, (cfg, err)       # fp16 hi/lo split: ~2^-22 per product
 
 
 def test_conv_tc_residual_and_split_output():
-    assert _run(2, 32, 32, 120, 40, 1, 1, 0, with_res=True) < 2e-6
-    assert _run(2, 64, 64, 128, 128, 3, 1, 1, out_split=True) < 2e-6
-    assert _run(2, 16, 16, 672, 112, 1, 1, 0, with_bias=False, with_res=True, out_split=True) < 2e-6
+    assert _run(2, 32, 32, 120, 40, 1, 1, 0, with_res=True) < 3e-6
+    assert _run(2, 64, 64, 128, 128, 3, 1, 1, out_split=True) < 3e-6
+    assert _run(2, 16, 16, 672, 112, 1, 1, 0, with_bias=False, with_res=True, out_split=True) < 3e-6
