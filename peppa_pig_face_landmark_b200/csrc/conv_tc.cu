@@ -237,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 float v[32];
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 const int co0 = co_tile + c0;
-                const int nvalid = min(32, p.Cout - co0);
+                const int nvalid = min(min(32, p.n_tile - c0), p.Cout - co0);     // n_tile need not be a multiple of 32
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (j < nvalid) {
