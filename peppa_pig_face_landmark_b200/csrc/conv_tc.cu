@@ -107,10 +107,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 constexpr int TC_BM = 128;            // pixels per tile (UMMA M)
 constexpr int TC_BK = 64;             // channels per k-block (one 128-byte swizzle atom of fp16)
 constexpr int A_TILE_BYTES = TC_BM * TC_BK * 2;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 4;
 
+template <int ACT>
+__device__ __forceinline__ float act_t(float v) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == ACT_HSWISH) return v * hsigmoid_f(v);
+    if (ACT == ACT_SIGMOID) return sigmoid_f(v);
+    if (ACT == ACT_SILU) return v * sigmoid_f(v);
+    if (ACT == ACT_HSIGMOID) return hsigmoid_f(v);
+    return v;
+}
+// dynamic index into a register array without forcing it to local memory
+__device__ __forceinline__ float v_at(const float* v, int j) {
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) r = (j == i) ? v[i] : r;
+    return r;
+}
+
+template <int ACT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcK p) {
@@ -136,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(&tfull_bar[a]), 1);
-            mbar_init(smem_u32(&tempty_bar[a]), 4);          // one arrival per epilogue warp
+            mbar_init(smem_u32(&tempty_bar[a]), 8);          // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -200,8 +218,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
                     const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
                     const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + b_tile_bytes);
-#pragma unroll
-                    for (int k = 0; k < TC_BK / 16; ++k) {
+                    // only the 16-channel steps that hold real channels (TMA zero-fills the rest)
+                    const int cc = kb % p.cchunks;
+                    const int ksteps = min(TC_BK / 16, (p.Cin - cc * TC_BK + 15) / 16);
+                    for (int k = 0; k < ksteps; ++k) {
                         const uint64_t koff = (uint64_t)(k * 32 >> 4);       // 16 fp16 = 32 bytes along K
                         // small terms first, then the dominant hi*hi product
                         umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
@@ -217,88 +237,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ================================================================== epilogue (warps 4-7 = TMEM lane quarters 0-3)
+        // ================================================================== epilogue
+        // 8 warps: warp%4 selects the TMEM lane quarter (hardware rule), (warp-4)/4 the odd/even
+        // 32-column chunks.  One thread = one output pixel x 32 consecutive channels per chunk.
         const int q = warp & 3;
+        const int half_id = (warp - 4) >> 2;
         const int row = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        const int tiles_x = p.W / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
             const int img = m_idx / p.tiles_per_img;
             const int t = m_idx - img * p.tiles_per_img;
-            const int tiles_x = p.W / p.bw;
             const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
             const long long pix = ((long long)img * p.H + y) * p.W + x;
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
             const int co_tile = n_idx * p.n_tile;
-            for (int c0 = 0; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 32) {
+            for (int c0 = half_id * 32; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 64) {
                 float v[32];
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 const int co0 = co_tile + c0;
-                const int nvalid = min(min(32, p.n_tile - c0), p.Cout - co0);     // n_tile need not be a multiple of 32
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nvalid) {
-                        float b = p.bias ? __ldg(p.bias + co0 + j) : 0.f;
-                        v[j] = apply_act(v[j] * p.out_scale + b, p.act);
-                    }
-                }
-                if (p.res) {
-                    if (p.res_fmt == DT_SPLIT16) {
-                        const __half* rh = (const __half*)p.res + pix * p.res_ld + p.res_coff + co0;
-                        const __half* rl = rh + p.res_plane;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
-                    } else {
-                        const float* r = (const float*)p.res + pix * p.res_ld + p.res_coff + co0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) v[j] += r[j];
-                    }
-                }
-                if (p.out_fmt == DT_SPLIT16) {
-                    __half* oh = (__half*)p.out + pix * p.out_ld + p.out_coff;
-                    __half* ol = oh + p.out_plane;
-                    const bool vec = p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 7) == 0;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (g * 8 >= nvalid) break;
-                        __half hh[8], ll[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float f = v[g * 8 + j];
-                            hh[j] = __float2half_rn(f);
-                            ll[j] = __float2half_rn(f - __half2float(hh[j]));
-                        }
-                        if (vec && g * 8 + 8 <= nvalid) {
-                            *reinterpret_cast<uint4*>(oh + co0 + g * 8) = *reinterpret_cast<const uint4*>(hh);
-                            *reinterpret_cast<uint4*>(ol + co0 + g * 8) = *reinterpret_cast<const uint4*>(ll);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                if (g * 8 + j < nvalid) {
-                                    oh[(long long)(co0 + g * 8 + j) * p.out_cstride] = hh[j];
-                                    ol[(long long)(co0 + g * 8 + j) * p.out_cstride] = ll[j];
-                                }
-                        }
-                    }
-                } else {
-                    float* o = (float*)p.out + pix * p.out_ld + p.out_coff;
-                    const bool vec = p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 3) == 0;
+                const int nvalid = min(min(32, p.n_tile - c0), p.Cout - co0);   // n_tile need not be a multiple of 32
+                const long long o_el = pix * p.out_ld + p.out_coff + co0;
+                const bool fast = nvalid == 32 && p.out_cstride == 1 &&
+                                  (OUT_SPLIT ? (((p.out_ld | (p.out_coff + co0)) & 7) == 0)
+                                             : (((p.out_ld | (p.out_coff + co0)) & 3) == 0));
+                if (fast) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0);
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
-                        if (g * 4 >= nvalid) break;
-                        if (vec && g * 4 + 4 <= nvalid) {
-                            *reinterpret_cast<float4*>(o + co0 + g * 4) =
-                                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                        } else {
+                        const float4 bb = __ldg(b4 + g);
+                        v[4 * g + 0] = act_t<ACT>(fmaf(v[4 * g + 0], p.out_scale, bb.x));
+                        v[4 * g + 1] = act_t<ACT>(fmaf(v[4 * g + 1], p.out_scale, bb.y));
+                        v[4 * g + 2] = act_t<ACT>(fmaf(v[4 * g + 2], p.out_scale, bb.z));
+                        v[4 * g + 3] = act_t<ACT>(fmaf(v[4 * g + 3], p.out_scale, bb.w));
+                    }
+                    if (p.res) {
+                        const long long r_el = pix * p.res_ld + p.res_coff + co0;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                if (g * 4 + j < nvalid) o[(long long)(co0 + g * 4 + j) * p.out_cstride] = v[g * 4 + j];
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 r = ld4(p.res, p.res_fmt, p.res_plane, r_el + 4 * g);
+                            v[4 * g + 0] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
                         }
+                    }
+                    if (OUT_SPLIT) {
+                        __half* oh = (__half*)p.out + o_el;
+                        __half* ol = oh + p.out_plane;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint4 hv, lv;
+                            uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+                            uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float a0 = v[8 * g + 2 * j], a1 = v[8 * g + 2 * j + 1];
+                                const __half2 h2 = __floats2half2_rn(a0, a1);
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                                hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                            *reinterpret_cast<uint4*>(oh + 8 * g) = hv;
+                            *reinterpret_cast<uint4*>(ol + 8 * g) = lv;
+                        }
+                    } else {
+                        float* o = (float*)p.out + o_el;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            *reinterpret_cast<float4*>(o + 4 * g) =
+                                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    }
+                } else {
+                    // ragged tail / strided or unaligned destination: scalar, not unrolled (rare)
+                    const long long r_el = pix * p.res_ld + p.res_coff + co0;
+#pragma unroll 1
+                    for (int j = 0; j < nvalid; ++j) {
+                        float f = act_t<ACT>(fmaf(v_at(v, j), p.out_scale, __ldg(p.bias + co0 + j)));
+                        if (p.res) f += ld1(p.res, p.res_fmt, p.res_plane, r_el + j);
+                        st1(p.out, OUT_SPLIT ? DT_SPLIT16 : DT_F32, p.out_plane,
+                            pix * p.out_ld + p.out_coff + (long long)(co0 + j) * p.out_cstride, f);
                     }
                 }
             }
@@ -333,6 +353,15 @@ static EncodeTiledFn get_encode() {
             fn = (EncodeTiledFn)p;
     }
     return fn;
+}
+
+static const float* zero_bias() {
+    static float* z = nullptr;       // 1024 zeros for bias-free layers (ASPP), per process/device
+    if (!z) {
+        if (cudaMalloc(&z, 1024 * sizeof(float)) != cudaSuccess) return nullptr;
+        cudaMemset(z, 0, 1024 * sizeof(float));
+    }
+    return z;
 }
 
 bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff) {
@@ -389,15 +418,25 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
-    k.bias = s.bias;
+    k.bias = s.bias ? s.bias : zero_bias();
+    SKPS_CHECK(k.bias, "conv_tc: zero-bias allocation failed");
+    k.Cin = s.Cin;
     k.out = s.out; k.out_fmt = s.out_fmt; k.out_plane = s.out_plane; k.out_ld = s.out_ld; k.out_coff = s.out_coff;
     k.out_cstride = s.out_cstride;
     k.res = s.res; k.res_fmt = s.res_fmt; k.res_plane = s.res_plane; k.res_ld = s.res_ld; k.res_coff = s.res_coff;
+    return 0;
+}
+
+template <int ACT, bool SPLIT>
+static int tc_launch_t(const TcLayer& L, const TcK& k, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        SKPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+        SKPS_CUDA(cudaFuncSetAttribute(conv_tc_kernel<ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024 - 1024));
         attr_set = true;
     }
+    conv_tc_kernel<ACT, SPLIT><<<grid, TC_THREADS, L.smem_bytes, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, k);
+    SKPS_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -406,9 +445,16 @@ int tc_launch(const TcLayer& L, int batch, int num_sms, cudaStream_t stream) {
     k.m_tiles = batch * k.tiles_per_img;
     int total = k.m_tiles * k.n_tiles;
     int grid = total < num_sms ? total : num_sms;
-    conv_tc_kernel<<<grid, TC_THREADS, L.smem_bytes, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, k);
-    SKPS_CUDA(cudaGetLastError());
-    return 0;
+    const bool sp = k.out_fmt == DT_SPLIT16;
+    switch (k.act) {
+        case ACT_NONE: return sp ? tc_launch_t<ACT_NONE, true>(L, k, grid, stream) : tc_launch_t<ACT_NONE, false>(L, k, grid, stream);
+        case ACT_RELU: return sp ? tc_launch_t<ACT_RELU, true>(L, k, grid, stream) : tc_launch_t<ACT_RELU, false>(L, k, grid, stream);
+        case ACT_HSWISH: return sp ? tc_launch_t<ACT_HSWISH, true>(L, k, grid, stream) : tc_launch_t<ACT_HSWISH, false>(L, k, grid, stream);
+        case ACT_SIGMOID: return sp ? tc_launch_t<ACT_SIGMOID, true>(L, k, grid, stream) : tc_launch_t<ACT_SIGMOID, false>(L, k, grid, stream);
+        default: break;
+    }
+    set_error("conv_tc: activation %d not instantiated", k.act);
+    return 1;
 }
 
 // float32 NHWC -> hi/lo float16 planes (used by the debug entry point and by f32->split conversions)

@@ -9,7 +9,7 @@ namespace skps {
 struct TcK {                     // kernel parameters
     int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
     int taps, kw, dil, pad, cchunks;
-    int Cout, act, stages;
+    int Cout, Cin, act, stages;
     float out_scale;             // exact power of two undoing the weight pre-scale
     const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;

@@ -345,7 +345,10 @@ class _Lowerer:
             parent, off, stride = t.home
             t.view = self.view(parent).sub(off, t.C, stride)
         else:
-            b = self.plan.new_buf(t.C, t.H, t.W, t.dtype, name)
+            # pixel rows of odd width (the 294-channel heat map) are padded to a multiple of 8 channels so
+            # every kernel can use 16-byte vector stores; the view keeps the logical channel count
+            ld = t.C if (t.C % 8 == 0 or t.C <= 8 or t.H * t.W == 1) else -(-t.C // 8) * 8
+            b = self.plan.new_buf(ld, t.H, t.W, t.dtype, name)
             t.view = P.View(b, 0, 1, t.C)
         return t.view
 
