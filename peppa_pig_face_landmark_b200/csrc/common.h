@@ -144,6 +144,8 @@ struct ConvArgs {
     int kh, kw, sh, sw, ph, pw, dh, dw, act, in_u8, batch;
 };
 int launch_conv(const ConvArgs& a, cudaStream_t s);
+bool stem_conv_supported(const ConvArgs& a);
+int launch_stem_conv(const ConvArgs& a, cudaStream_t s);
 
 struct DwArgs {
     TView in, out;

@@ -262,53 +262,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const int co0 = co_tile + c0;
                 const int nvalid = min(min(32, p.n_tile - c0), p.Cout - co0);   // n_tile need not be a multiple of 32
                 const long long o_el = pix * p.out_ld + p.out_coff + co0;
-                const bool fast = nvalid == 32 && p.out_cstride == 1 &&
-                                  (OUT_SPLIT ? (((p.out_ld | (p.out_coff + co0)) & 7) == 0)
-                                             : (((p.out_ld | (p.out_coff + co0)) & 3) == 0));
+                // vector path: whole groups of 8 channels (every Cout in the network but the 294-wide heat map and
+                // the 1-channel sSE map is a multiple of 8), unit channel stride, 16-byte aligned destination
+                const bool fast = (nvalid & 7) == 0 && p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 7) == 0;
                 if (fast) {
+                    const int ng = nvalid >> 3;                       // warp-uniform
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0);
+                    const long long r_el = pix * p.res_ld + p.res_coff + co0;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const float4 bb = __ldg(b4 + g);
-                        v[4 * g + 0] = act_t<ACT>(fmaf(v[4 * g + 0], p.out_scale, bb.x));
-                        v[4 * g + 1] = act_t<ACT>(fmaf(v[4 * g + 1], p.out_scale, bb.y));
-                        v[4 * g + 2] = act_t<ACT>(fmaf(v[4 * g + 2], p.out_scale, bb.z));
-                        v[4 * g + 3] = act_t<ACT>(fmaf(v[4 * g + 3], p.out_scale, bb.w));
-                    }
-                    if (p.res) {
-                        const long long r_el = pix * p.res_ld + p.res_coff + co0;
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 r = ld4(p.res, p.res_fmt, p.res_plane, r_el + 4 * g);
-                            v[4 * g + 0] += r.x; v[4 * g + 1] += r.y; v[4 * g + 2] += r.z; v[4 * g + 3] += r.w;
-                        }
-                    }
-                    if (OUT_SPLIT) {
-                        __half* oh = (__half*)p.out + o_el;
-                        __half* ol = oh + p.out_plane;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 hv, lv;
-                            uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
-                            uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float a0 = v[8 * g + 2 * j], a1 = v[8 * g + 2 * j + 1];
-                                const __half2 h2 = __floats2half2_rn(a0, a1);
-                                const float2 hf = __half22float2(h2);
-                                const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-                                hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
-                                lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    for (int g = 0; g < 4; ++g) {
+                        if (g < ng) {
+                            float* w = v + 8 * g;
+                            const float4 b0 = __ldg(b4 + 2 * g), b1 = __ldg(b4 + 2 * g + 1);
+                            w[0] = act_t<ACT>(fmaf(w[0], p.out_scale, b0.x)); w[1] = act_t<ACT>(fmaf(w[1], p.out_scale, b0.y));
+                            w[2] = act_t<ACT>(fmaf(w[2], p.out_scale, b0.z)); w[3] = act_t<ACT>(fmaf(w[3], p.out_scale, b0.w));
+                            w[4] = act_t<ACT>(fmaf(w[4], p.out_scale, b1.x)); w[5] = act_t<ACT>(fmaf(w[5], p.out_scale, b1.y));
+                            w[6] = act_t<ACT>(fmaf(w[6], p.out_scale, b1.z)); w[7] = act_t<ACT>(fmaf(w[7], p.out_scale, b1.w));
+                            if (p.res) {
+                                const float4 r0 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g);
+                                const float4 r1 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g + 4);
+                                w[0] += r0.x; w[1] += r0.y; w[2] += r0.z; w[3] += r0.w;
+                                w[4] += r1.x; w[5] += r1.y; w[6] += r1.z; w[7] += r1.w;
                             }
-                            *reinterpret_cast<uint4*>(oh + 8 * g) = hv;
-                            *reinterpret_cast<uint4*>(ol + 8 * g) = lv;
-                        }
-                    } else {
-                        float* o = (float*)p.out + o_el;
+                            if (OUT_SPLIT) {
+                                __half* oh = (__half*)p.out + o_el + 8 * g;
+                                uint4 hv, lv;
+                                uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+                                uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g)
-                            *reinterpret_cast<float4*>(o + 4 * g) =
-                                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                                for (int j = 0; j < 4; ++j) {
+                                    const float a0 = w[2 * j], a1 = w[2 * j + 1];
+                                    const __half2 h2 = __floats2half2_rn(a0, a1);
+                                    const float2 hf = __half22float2(h2);
+                                    const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                                    hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                                    lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                                }
+                                *reinterpret_cast<uint4*>(oh) = hv;
+                                *reinterpret_cast<uint4*>(oh + p.out_plane) = lv;
+                            } else {
+                                float* o = (float*)p.out + o_el + 8 * g;
+                                *reinterpret_cast<float4*>(o) = make_float4(w[0], w[1], w[2], w[3]);
+                                *reinterpret_cast<float4*>(o + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                            }
+                        }
                     }
                 } else {
                     // ragged tail / strided or unaligned destination: scalar, not unrolled (rare)

@@ -66,6 +66,78 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
     }
 }
 
+
+// Register-tiled variant: one thread = PX consecutive output pixels along x, 4 channels.  Each input row
+// segment is loaded once and reused by all taps and all PX outputs, which cuts global loads from
+// K*K to K*((PX-1)*S+(K-1)*D+1)/PX per output (3x3: 9 -> 4.5, 5x5: 25 -> 10).
+template <int K, int S, int D, int PX>
+__global__ void __launch_bounds__(128) dwconv_tiled_kernel(const DwK p) {
+    constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    const int C4 = p.C >> 2;
+    const int WoT = p.Wo / PX;
+    int c = (int)(i % C4) * 4;
+    long long r = i / C4;
+    int oxb = (int)(r % WoT) * PX;
+    long long t = r / WoT;
+    int oy = (int)(t % p.Ho);
+    int n = (int)(t / p.Ho);
+    const float4 bias = *reinterpret_cast<const float4*>(p.bias + c);
+    float4 acc[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) acc[q] = bias;
+    const int iy0 = oy * S - p.ph, ix0 = oxb * S - p.pw;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = iy0 + ky * D;
+        if (iy < 0 || iy >= p.H) continue;
+        float4 in[SPAN];
+        const long long rowbase = (((long long)n * p.H + iy) * p.W) * p.in_ld + p.in_coff + c;
+#pragma unroll
+        for (int j = 0; j < SPAN; ++j) {
+            // only the columns some tap actually reads (dilated kernels skip every other one)
+            bool used = false;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == j);
+            const int ix = ix0 + j;
+            in[j] = (used && ix >= 0 && ix < p.W) ? ld4(p.in, p.in_fmt, p.in_plane, rowbase + (long long)ix * p.in_ld)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.C + c);
+#pragma unroll
+            for (int q = 0; q < PX; ++q) {
+                const float4 v = in[q * S + kx * D];
+                acc[q].x = fmaf(v.x, w.x, acc[q].x);
+                acc[q].y = fmaf(v.y, w.y, acc[q].y);
+                acc[q].z = fmaf(v.z, w.z, acc[q].z);
+                acc[q].w = fmaf(v.w, w.w, acc[q].w);
+            }
+        }
+    }
+    const long long obase = ((((long long)n * p.Ho + oy) * p.Wo) + oxb) * p.out_ld + p.out_coff + c;
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+        float4 a = acc[q];
+        a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
+        a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+        st4(p.out, p.out_fmt, p.out_plane, obase + (long long)q * p.out_ld, a);
+    }
+}
+
+template <int K, int S, int D>
+static int launch_dw_tiled(DwK k, int batch, cudaStream_t s) {
+    constexpr int PX = 4;
+    k.total = (long long)batch * k.Ho * (k.Wo / PX) * (k.C / 4);
+    dwconv_tiled_kernel<K, S, D, PX><<<blocks_for(k.total, 128), 128, 0, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_dwconv(const DwArgs& a, cudaStream_t s) {
     DwK k;
     k.in = a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.H = a.in.H; k.W = a.in.W;
@@ -78,6 +150,14 @@ int launch_dwconv(const DwArgs& a, cudaStream_t s) {
     SKPS_CHECK(a.in.c_stride == 1 && a.in.C == a.out.C, "dwconv: bad input view");
     SKPS_CHECK(k.C % 4 == 0 && k.in_ld % 4 == 0 && k.in_coff % 4 == 0, "dwconv: C/ld/offset must be multiples of 4");
     SKPS_CHECK(k.out_cstride != 1 || (k.out_ld % 4 == 0 && k.out_coff % 4 == 0), "dwconv: unaligned output view");
+    const bool square = a.kh == a.kw && a.sh == a.sw && a.dh == a.dw && a.ph == a.pw;
+    if (square && k.out_cstride == 1 && k.Wo % 4 == 0) {
+        if (a.kh == 3 && a.sh == 1 && a.dh == 1) return launch_dw_tiled<3, 1, 1>(k, a.batch, s);
+        if (a.kh == 3 && a.sh == 2 && a.dh == 1) return launch_dw_tiled<3, 2, 1>(k, a.batch, s);
+        if (a.kh == 5 && a.sh == 1 && a.dh == 1) return launch_dw_tiled<5, 1, 1>(k, a.batch, s);
+        if (a.kh == 5 && a.sh == 2 && a.dh == 1) return launch_dw_tiled<5, 2, 1>(k, a.batch, s);
+        if (a.kh == 5 && a.sh == 1 && a.dh == 2) return launch_dw_tiled<5, 1, 2>(k, a.batch, s);
+    }
     k.total = (long long)a.batch * k.Ho * k.Wo * (k.C / 4);
     dwconv_kernel<<<blocks_for(k.total, 256), 256, 0, s>>>(k);
     SKPS_CUDA(cudaGetLastError());
@@ -151,6 +231,66 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
 }
 #undef SRC
 
+
+// 4-channel vector variant of the kernels above (modes 2-6) for unit-stride, 16-byte aligned views.
+__device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 y) {
+    return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+__device__ __forceinline__ float4 f4_scale(float a, float4 x) { return make_float4(a * x.x, a * x.y, a * x.z, a * x.w); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) elementwise4_kernel(const EwK p) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    const int C4 = p.C >> 2;
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int ox = (int)(pix % p.Wo);
+    long long t = pix / p.Wo;
+    int oy = (int)(t % p.Ho);
+    int n = (int)(t / p.Ho);
+    const long long sbase = (long long)n * p.H * p.W * p.in_ld + p.in_coff + c;
+#define SRC4(off) ld4(p.in, p.in_fmt, p.in_plane, sbase + (off))
+    float4 v;
+    if (MODE == 2) {
+        float sy = fmaxf((oy + 0.5f) * 0.5f - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * 0.5f - 0.5f, 0.f);
+        int y0 = (int)sy, x0 = (int)sx;
+        int y1 = min(y0 + 1, p.H - 1), x1 = min(x0 + 1, p.W - 1);
+        float ly = sy - y0, lx = sx - x0;
+        float hy = 1.f - ly, hx = 1.f - lx;
+        float4 p00 = SRC4(((long long)y0 * p.W + x0) * p.in_ld), p01 = SRC4(((long long)y0 * p.W + x1) * p.in_ld);
+        float4 p10 = SRC4(((long long)y1 * p.W + x0) * p.in_ld), p11 = SRC4(((long long)y1 * p.W + x1) * p.in_ld);
+        float4 top = f4_fma(hx, p00, f4_scale(lx, p01)), bot = f4_fma(hx, p10, f4_scale(lx, p11));
+        v = f4_fma(hy, top, f4_scale(ly, bot));
+    } else {
+        v = SRC4(((long long)oy * p.W + ox) * p.in_ld);
+        if (MODE == 4) {
+            const float4 a = *reinterpret_cast<const float4*>((const float*)p.a + c);
+            const float4 b = *reinterpret_cast<const float4*>((const float*)p.b + c);
+            v.x = apply_act(fmaf(v.x, a.x, b.x), p.act); v.y = apply_act(fmaf(v.y, a.y, b.y), p.act);
+            v.z = apply_act(fmaf(v.z, a.z, b.z), p.act); v.w = apply_act(fmaf(v.w, a.w, b.w), p.act);
+        } else if (MODE == 5) {
+            const float4 cs = ld4(p.a, p.a_fmt, p.a_plane, (long long)n * p.a_ld + p.a_coff + c);
+            const float ss = ld1(p.b, p.b_fmt, p.b_plane,
+                                 ((long long)n * p.H * p.W + (long long)oy * p.W + ox) * p.b_ld + p.b_coff);
+            v.x = __fadd_rn(__fmul_rn(v.x, cs.x), __fmul_rn(v.x, ss));
+            v.y = __fadd_rn(__fmul_rn(v.y, cs.y), __fmul_rn(v.y, ss));
+            v.z = __fadd_rn(__fmul_rn(v.z, cs.z), __fmul_rn(v.z, ss));
+            v.w = __fadd_rn(__fmul_rn(v.w, cs.w), __fmul_rn(v.w, ss));
+        } else if (MODE == 6) {
+            const float4 g = ld4(p.a, p.a_fmt, p.a_plane, (long long)n * p.a_ld + p.a_coff + c);
+            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+        }
+    }
+#undef SRC4
+    st4(p.out, p.out_fmt, p.out_plane, pix * p.out_ld + p.out_coff + c, v);
+}
+
+static bool ew_vec_ok(const EwK& k) {
+    return k.C % 4 == 0 && k.in_cs == 1 && k.out_cs == 1 && ((k.in_ld | k.in_coff | k.out_ld | k.out_coff) & 3) == 0 &&
+           ((k.a_ld | k.a_coff) & 3) == 0;
+}
+
 static EwK make_ew(const TView& in, const TView& out, int batch) {
     EwK k = {};
     k.in = in.base; k.in_ld = in.ld; k.in_coff = in.c_off; k.in_cs = in.c_stride; k.H = in.H; k.W = in.W;
@@ -162,7 +302,12 @@ static EwK make_ew(const TView& in, const TView& out, int batch) {
 }
 
 #define LAUNCH_EW(MODE, k, s)                                                     \
-    elementwise_kernel<MODE><<<blocks_for((k).total, 256), 256, 0, s>>>(k);       \
+    if ((MODE) >= 2 && ew_vec_ok(k)) {                                            \
+        (k).total /= 4;                                                           \
+        elementwise4_kernel<(MODE) >= 2 ? (MODE) : 2><<<blocks_for((k).total, 256), 256, 0, s>>>(k);   \
+    } else {                                                                      \
+        elementwise_kernel<MODE><<<blocks_for((k).total, 256), 256, 0, s>>>(k);   \
+    }                                                                             \
     SKPS_CUDA(cudaGetLastError());                                                \
     return 0;
 
@@ -205,6 +350,90 @@ int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int bat
     EwK k = make_ew(x, out, batch);
     k.a = gate.base; k.a_ld = gate.ld; k.a_coff = gate.c_off; k.a_fmt = gate.fmt; k.a_plane = gate.plane;
     LAUNCH_EW(6, k, s)
+}
+
+
+// ------------------------------------------------------------------------------------------
+// First layer of both networks: 3x3 stride-2 conv on uint8 pixels, 3 -> 16 channels (+ act).
+// One thread = one output pixel x 16 channels; weights and the v/255 table live in shared memory.
+// (kps_student.onnx node 1, yolov5n-0.5.onnx node 0; /255 as in face_landmark.py:46, face_detector.py:67)
+// ------------------------------------------------------------------------------------------
+struct StemK {
+    const uint8_t* in; int H, W;
+    void* out; int out_fmt; long long out_plane; int out_ld, out_coff, Ho, Wo;
+    const float* w;       // [16][3][3][3]  (co, ky, kx, ci)
+    const float* bias;
+    int act; long long total;
+};
+
+__global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
+    __shared__ __align__(16) float sw[27][16];
+    __shared__ float lut[256];
+    for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i / 16][i % 16] = p.w[(i % 16) * 27 + i / 16];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.f);
+    __syncthreads();
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.total) return;
+    int ox = (int)(i % p.Wo);
+    long long t = i / p.Wo;
+    int oy = (int)(t % p.Ho);
+    int n = (int)(t / p.Ho);
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    const uint8_t* img = p.in + (long long)n * p.H * p.W * 3;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int iy = oy * 2 - 1 + ky;
+        if (iy < 0 || iy >= p.H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int ix = ox * 2 - 1 + kx;
+            if (ix < 0 || ix >= p.W) continue;
+            const uint8_t* px = img + ((long long)iy * p.W + ix) * 3;
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float x = lut[px[ci]];
+                const float4* wr = reinterpret_cast<const float4*>(sw[(ky * 3 + kx) * 3 + ci]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 w = wr[g];
+                    acc[4 * g + 0] = fmaf(x, w.x, acc[4 * g + 0]);
+                    acc[4 * g + 1] = fmaf(x, w.y, acc[4 * g + 1]);
+                    acc[4 * g + 2] = fmaf(x, w.z, acc[4 * g + 2]);
+                    acc[4 * g + 3] = fmaf(x, w.w, acc[4 * g + 3]);
+                }
+            }
+        }
+    }
+    const long long o = i * p.out_ld + p.out_coff;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        float4 v;
+        v.x = apply_act(acc[4 * g + 0] + p.bias[4 * g + 0], p.act);
+        v.y = apply_act(acc[4 * g + 1] + p.bias[4 * g + 1], p.act);
+        v.z = apply_act(acc[4 * g + 2] + p.bias[4 * g + 2], p.act);
+        v.w = apply_act(acc[4 * g + 3] + p.bias[4 * g + 3], p.act);
+        st4(p.out, p.out_fmt, p.out_plane, o + 4 * g, v);
+    }
+}
+
+bool stem_conv_supported(const ConvArgs& a) {
+    return a.in_u8 && a.in.C == 3 && a.in.ld == 3 && a.out.C == 16 && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2 &&
+           a.ph == 1 && a.pw == 1 && a.dh == 1 && a.dw == 1 && !a.res.base && !a.gate.base && a.bias &&
+           a.out.c_stride == 1 && ((a.out.ld | a.out.c_off) & 3) == 0;
+}
+
+int launch_stem_conv(const ConvArgs& a, cudaStream_t s) {
+    StemK k;
+    k.in = (const uint8_t*)a.in.base; k.H = a.in.H; k.W = a.in.W;
+    k.out = a.out.base; k.out_fmt = a.out.fmt; k.out_plane = a.out.plane; k.out_ld = a.out.ld; k.out_coff = a.out.c_off;
+    k.Ho = a.out.H; k.Wo = a.out.W;
+    k.w = a.w; k.bias = a.bias; k.act = a.act;
+    k.total = (long long)a.batch * k.Ho * k.Wo;
+    stem_conv_kernel<<<blocks_for(k.total, 128), 128, 0, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,24 @@
+"""Summarise an ncu launch list (gpu__time_duration.sum, one student forward) per plan op."""
+import csv, sys, os
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from collections import defaultdict
+from peppa_pig_face_landmark_b200 import lowering, plan as P
+path = sys.argv[1]
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+lines = [l for l in open(path) if not l.startswith('==')]
+rows = list(csv.DictReader(lines))
+pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/kps_student.onnx'), (256, 256))
+assert len(rows) == len(pl.ops), (len(rows), len(pl.ops))
+out, tot, d = [], 0.0, defaultdict(float)
+for i, (row, op) in enumerate(zip(rows, pl.ops)):
+    t = float(row['Metric Value']) / 1e3
+    tot += t
+    o = op.outs[0]
+    kind = P.OP_NAMES[op.type] + ('/TC' if op.flags & 2 else '')
+    d[kind] += t
+    out.append((t, i, kind, op.ins[0].C, o.C, o.H, op.k[0], op.name[-44:]))
+print('total %.1f us over %d launches' % (tot, len(rows)))
+for x in sorted(out, reverse=True)[:top]:
+    print('%9.1f us  #%-3d %-22s cin=%-4d cout=%-4d H=%-4d k=%d %s' % x)
+print({k: round(v, 1) for k, v in sorted(d.items(), key=lambda kv: -kv[1])})
