@@ -62,6 +62,14 @@ class PlanInterp:
                 y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b), stride=op.s, padding=tuple(op.p),
                              dilation=op.d, groups=C)
                 wr(op.outs[0], _act(y, op.act).permute(0, 2, 3, 1))
+            elif t == P.OP_UPCAT_DW:
+                low = rd(op.ins[0]).permute(0, 3, 1, 2)
+                up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False)
+                x = torch.cat([up, rd(op.ins[1]).permute(0, 3, 1, 2)], 1)
+                C = x.shape[1]
+                w = torch.from_numpy(op.w).T.reshape(C, 1, 3, 3).contiguous()
+                y = F.conv2d(x, w, torch.from_numpy(op.b), padding=1, groups=C)
+                wr(op.outs[0], _act(y, op.act).permute(0, 2, 3, 1))
             elif t == P.OP_MAXPOOL2:
                 x = rd(op.ins[0]).permute(0, 3, 1, 2)
                 wr(op.outs[0], F.max_pool2d(x, 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1))

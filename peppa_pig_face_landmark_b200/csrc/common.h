@@ -11,7 +11,7 @@ namespace skps {
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
-    OP_SCALE_CH = 12
+    OP_SCALE_CH = 12, OP_UPCAT_DW = 13
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
@@ -136,6 +136,52 @@ __device__ __forceinline__ void st4(void* base, int fmt, long long plane, long l
     }
 }
 
+// 8 consecutive elements, i a multiple of 8 (one 16-byte load per float16 plane)
+struct float8 { float v[8]; };
+__device__ __forceinline__ float8 ld8(const void* base, int fmt, long long plane, long long i) {
+    float8 r;
+    if (fmt == DT_SPLIT16) {
+        const __half* h = (const __half*)base;
+        const uint4 a = *reinterpret_cast<const uint4*>(h + i), b = *reinterpret_cast<const uint4*>(h + i + plane);
+        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 x = __half22float2(a2[j]), y = __half22float2(b2[j]);
+            r.v[2 * j] = x.x + y.x;
+            r.v[2 * j + 1] = x.y + y.y;
+        }
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>((const float*)base + i);
+        const float4 b = *reinterpret_cast<const float4*>((const float*)base + i + 4);
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+        r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void st8(void* base, int fmt, long long plane, long long i, const float8& r) {
+    if (fmt == DT_SPLIT16) {
+        __half* h = (__half*)base;
+        uint4 hv, lv;
+        uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+        uint32_t* lp = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __half2 h2 = __floats2half2_rn(r.v[2 * j], r.v[2 * j + 1]);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(r.v[2 * j] - hf.x, r.v[2 * j + 1] - hf.y);
+            hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        *reinterpret_cast<uint4*>(h + i) = hv;
+        *reinterpret_cast<uint4*>(h + i + plane) = lv;
+    } else {
+        float* f = (float*)base + i;
+        *reinterpret_cast<float4*>(f) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+        *reinterpret_cast<float4*>(f + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    }
+}
+
 // ---- kernel launchers (defined in the .cu files) ---------------------------------------------
 struct ConvArgs {
     TView in, out, res, gate;     // res.base / gate.base may be null
@@ -154,6 +200,9 @@ struct DwArgs {
     int kh, kw, sh, sw, ph, pw, dh, dw, act, batch;
 };
 int launch_dwconv(const DwArgs& a, cudaStream_t s);
+// depthwise 3x3 over concat(bilinear-x2(low), skip) without materialising the upsampled tensor
+int launch_upcat_dw(const TView& low, const TView& skip, const TView& out, const float* w, const float* bias, int act,
+                    int batch, cudaStream_t s);
 
 int launch_maxpool2(const TView& in, const TView& out, int batch, cudaStream_t s);
 int launch_resize_nearest(const TView& in, const TView& out, int batch, cudaStream_t s);

@@ -114,6 +114,7 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
             case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
+            case OP_UPCAT_DW: rc = launch_upcat_dw(in0, in1, out0, w, b, op.act, batch, s); break;
             case OP_DET_DECODE: {
                 TView heads[3] = {in0, in1, in2};
                 rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);

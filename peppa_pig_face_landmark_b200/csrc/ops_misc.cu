@@ -7,9 +7,9 @@
 namespace skps {
 
 static inline int blocks_for(long long n, int threads) {
-    long long b = (n + threads - 1) / threads;
-    if (b > (1LL << 30)) b = 1LL << 30;
-    return (int)b;
+    // kernels index threads with 32-bit ints; every tensor here is far below 2^31 elements
+    if (n >= (1LL << 31) - threads) n = (1LL << 31) - threads - 1;
+    return (int)((n + threads - 1) / threads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -25,15 +25,15 @@ struct DwK {
 };
 
 __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
     const int C4 = p.C >> 2;
-    int c = (int)(i % C4) * 4;
-    long long pix = i / C4;
-    int ox = (int)(pix % p.Wo);
-    long long t = pix / p.Wo;
-    int oy = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
+    int c = (i % C4) * 4;
+    int pix = i / C4;
+    int ox = pix % p.Wo;
+    int t = pix / p.Wo;
+    int oy = t % p.Ho;
+    int n = t / p.Ho;
     float4 acc = *reinterpret_cast<const float4*>(p.bias + c);
     const int iy0 = oy * p.sh - p.ph, ix0 = ox * p.sw - p.pw;
     for (int ky = 0; ky < p.kh; ++ky) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
     acc.y = apply_act(acc.y, p.act);
     acc.z = apply_act(acc.z, p.act);
     acc.w = apply_act(acc.w, p.act);
-    const long long o = pix * p.out_ld + p.out_coff;
+    const long long o = (long long)pix * p.out_ld + p.out_coff;
     if (p.out_cstride == 1) {
         st4(p.out, p.out_fmt, p.out_plane, o + c, acc);
     } else {
@@ -73,16 +73,16 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwK p) {
 template <int K, int S, int D, int PX>
 __global__ void __launch_bounds__(128) dwconv_tiled_kernel(const DwK p) {
     constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
     const int C4 = p.C >> 2;
     const int WoT = p.Wo / PX;
-    int c = (int)(i % C4) * 4;
-    long long r = i / C4;
-    int oxb = (int)(r % WoT) * PX;
-    long long t = r / WoT;
-    int oy = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
+    int c = (i % C4) * 4;
+    int r = i / C4;
+    int oxb = (r % WoT) * PX;
+    int t = r / WoT;
+    int oy = t % p.Ho;
+    int n = t / p.Ho;
     const float4 bias = *reinterpret_cast<const float4*>(p.bias + c);
     float4 acc[PX];
 #pragma unroll
@@ -164,6 +164,154 @@ int launch_dwconv(const DwArgs& a, cudaStream_t s) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Decoder block head (model.py:133-196 DecoderBlock; kps_student.onnx nodes 176-178, 193-195):
+//   depthwise3x3( concat( bilinear_x2(low), skip ) )
+// computed without ever writing the up-sampled tensor: each thread interpolates the 3x3 high-res
+// neighbourhood it needs from a 3x3 low-res patch (half_pixel, align_corners=False), zero outside
+// the high-res image (the conv's padding).  One thread = one output pixel x 8 channels.
+// ------------------------------------------------------------------------------------------
+struct UpcatK {
+    const void* low; int low_fmt; long long low_plane; int low_ld, low_coff, Hl, Wl, Cu;
+    const void* skip; int skip_fmt; long long skip_plane; int skip_ld, skip_coff;
+    void* out; int out_fmt; long long out_plane; int out_ld, out_coff, H, W, C;
+    const float* w; const float* bias; int act; long long total;
+};
+
+__global__ void __launch_bounds__(128) upcat_dw_kernel(const UpcatK p) {
+    // one thread = a 2x2 block of output pixels x 4 channels.  All four outputs share one 3x3 low-res
+    // patch, and the 4x4 high-res neighbourhood they read is a fixed-weight (.25/.75) blend of it.
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
+    const int C4 = p.C >> 2;
+    int c = (i % C4) * 4;
+    int blk = i / C4;
+    const int Wb = p.W >> 1, Hb = p.H >> 1;
+    int bx = blk % Wb;
+    int t = blk / Wb;
+    int by = t % Hb;
+    int n = t / Hb;
+    const float4 bias = *reinterpret_cast<const float4*>(p.bias + c);
+    float4 acc[2][2] = {{bias, bias}, {bias, bias}};
+    float4 w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(p.w + k * p.C + c);
+    const int oy0 = by * 2, ox0 = bx * 2;
+    if (c >= p.Cu) {
+        // skip-connection channels: plain depthwise 3x3 on the 4x4 high-res window
+        const int cs = c - p.Cu;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int iy = oy0 - 1 + r;
+            if (iy < 0 || iy >= p.H) continue;
+            float4 row[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int ix = ox0 - 1 + q;
+                row[q] = (ix >= 0 && ix < p.W)
+                             ? ld4(p.skip, p.skip_fmt, p.skip_plane,
+                                   (((long long)n * p.H + iy) * p.W + ix) * p.skip_ld + p.skip_coff + cs)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int oy = 0; oy < 2; ++oy) {
+                const int ky = r - oy;
+                if (ky < 0 || ky > 2) continue;
+#pragma unroll
+                for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 v = row[ox + kx], ww = w[ky * 3 + kx];
+                        acc[oy][ox].x = fmaf(v.x, ww.x, acc[oy][ox].x);
+                        acc[oy][ox].y = fmaf(v.y, ww.y, acc[oy][ox].y);
+                        acc[oy][ox].z = fmaf(v.z, ww.z, acc[oy][ox].z);
+                        acc[oy][ox].w = fmaf(v.w, ww.w, acc[oy][ox].w);
+                    }
+            }
+        }
+    } else {
+        // low-res patch rows by-1..by+1, cols bx-1..bx+1 (clamped); high-res col j in 0..3 (x = ox0-1+j):
+        //   j=0: .75*L0+.25*L1   j=1: .25*L0+.75*L1   j=2: .75*L1+.25*L2   j=3: .25*L1+.75*L2     (half_pixel x2)
+        // columns/rows outside the high-res image are the conv's zero padding
+        const float vx0 = ox0 > 0 ? 1.f : 0.f, vx3 = ox0 + 2 < p.W ? 1.f : 0.f;
+        const float vy0 = oy0 > 0 ? 1.f : 0.f, vy3 = oy0 + 2 < p.H ? 1.f : 0.f;
+        float4 Hh[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int ly = min(max(by - 1 + r, 0), p.Hl - 1);
+            float4 L[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int lx = min(max(bx - 1 + q, 0), p.Wl - 1);
+                L[q] = ld4(p.low, p.low_fmt, p.low_plane, (((long long)n * p.Hl + ly) * p.Wl + lx) * p.low_ld + p.low_coff + c);
+            }
+#define BLEND(dst, a, b, wa, wb, m)                                         \
+    dst.x = (m) * ((wa) * a.x + (wb) * b.x); dst.y = (m) * ((wa) * a.y + (wb) * b.y); \
+    dst.z = (m) * ((wa) * a.z + (wb) * b.z); dst.w = (m) * ((wa) * a.w + (wb) * b.w);
+            BLEND(Hh[r][0], L[0], L[1], 0.75f, 0.25f, vx0)
+            BLEND(Hh[r][1], L[0], L[1], 0.25f, 0.75f, 1.f)
+            BLEND(Hh[r][2], L[1], L[2], 0.75f, 0.25f, 1.f)
+            BLEND(Hh[r][3], L[1], L[2], 0.25f, 0.75f, vx3)
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            // high-res row r (y = oy0-1+r) from patch rows: r=0: .75*H0+.25*H1, r=1: .25*H0+.75*H1, r=2: .75*H1+.25*H2, r=3: .25*H1+.75*H2
+            const int a = r >> 1;
+            const float wa = (r & 1) ? 0.25f : 0.75f, wb = 1.f - wa;
+            const float m = r == 0 ? vy0 : (r == 3 ? vy3 : 1.f);
+            float4 U[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { BLEND(U[j], Hh[a][j], Hh[a + 1][j], wa, wb, m) }
+#pragma unroll
+            for (int oy = 0; oy < 2; ++oy) {
+                const int ky = r - oy;
+                if (ky < 0 || ky > 2) continue;
+#pragma unroll
+                for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 v = U[ox + kx], ww = w[ky * 3 + kx];
+                        acc[oy][ox].x = fmaf(v.x, ww.x, acc[oy][ox].x);
+                        acc[oy][ox].y = fmaf(v.y, ww.y, acc[oy][ox].y);
+                        acc[oy][ox].z = fmaf(v.z, ww.z, acc[oy][ox].z);
+                        acc[oy][ox].w = fmaf(v.w, ww.w, acc[oy][ox].w);
+                    }
+            }
+        }
+#undef BLEND
+    }
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+            float4 v = acc[oy][ox];
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+            st4(p.out, p.out_fmt, p.out_plane,
+                (((long long)n * p.H + oy0 + oy) * p.W + ox0 + ox) * p.out_ld + p.out_coff + c, v);
+        }
+}
+
+int launch_upcat_dw(const TView& low, const TView& skip, const TView& out, const float* w, const float* bias, int act,
+                    int batch, cudaStream_t s) {
+    SKPS_CHECK(out.H == 2 * low.H && out.W == 2 * low.W && skip.H == out.H && skip.W == out.W &&
+               out.C == low.C + skip.C, "upcat_dw: shapes");
+    SKPS_CHECK(low.c_stride == 1 && skip.c_stride == 1 && out.c_stride == 1 &&
+               ((low.C | low.ld | low.c_off | skip.C | skip.ld | skip.c_off | out.ld | out.c_off) & 7) == 0,
+               "upcat_dw: views must be unit-stride and 8-channel aligned");
+    UpcatK k;
+    k.low = low.base; k.low_fmt = low.fmt; k.low_plane = low.plane; k.low_ld = low.ld; k.low_coff = low.c_off;
+    k.Hl = low.H; k.Wl = low.W; k.Cu = low.C;
+    k.skip = skip.base; k.skip_fmt = skip.fmt; k.skip_plane = skip.plane; k.skip_ld = skip.ld; k.skip_coff = skip.c_off;
+    k.out = out.base; k.out_fmt = out.fmt; k.out_plane = out.plane; k.out_ld = out.ld; k.out_coff = out.c_off;
+    k.H = out.H; k.W = out.W; k.C = out.C;
+    k.w = w; k.bias = bias; k.act = act;
+    k.total = (long long)batch * (out.H / 2) * (out.W / 2) * (out.C / 4);
+    upcat_dw_kernel<<<blocks_for(k.total, 128), 128, 0, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // Generic per-element kernels over (n, y, x, c) of the OUTPUT view.
 // ------------------------------------------------------------------------------------------
@@ -179,14 +327,14 @@ struct EwK {
 #define SRC(off) ld1(p.in, p.in_fmt, p.in_plane, sbase + (off))
 template <int MODE>   // 0 maxpool2 ceil, 1 nearest, 2 bilinear2x, 3 copy, 4 affine+act, 5 scse, 6 scale by gate[n,c]
 __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
-    int c = (int)(i % p.C);
-    long long pix = i / p.C;
-    int ox = (int)(pix % p.Wo);
-    long long t = pix / p.Wo;
-    int oy = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
+    int c = i % p.C;
+    int pix = i / p.C;
+    int ox = pix % p.Wo;
+    int t = pix / p.Wo;
+    int oy = t % p.Ho;
+    int n = t / p.Ho;
     const long long sbase = (long long)n * p.H * p.W * p.in_ld + p.in_coff + (long long)c * p.in_cs;
     float v;
     if (MODE == 0) {
@@ -227,7 +375,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
             v = v * ld1(p.a, p.a_fmt, p.a_plane, (long long)n * p.a_ld + p.a_coff + c);
         }
     }
-    st1(p.out, p.out_fmt, p.out_plane, pix * p.out_ld + p.out_coff + (long long)c * p.out_cs, v);
+    st1(p.out, p.out_fmt, p.out_plane, (long long)pix * p.out_ld + p.out_coff + (long long)c * p.out_cs, v);
 }
 #undef SRC
 
@@ -240,15 +388,15 @@ __device__ __forceinline__ float4 f4_scale(float a, float4 x) { return make_floa
 
 template <int MODE>
 __global__ void __launch_bounds__(256) elementwise4_kernel(const EwK p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
     const int C4 = p.C >> 2;
-    int c = (int)(i % C4) * 4;
-    long long pix = i / C4;
-    int ox = (int)(pix % p.Wo);
-    long long t = pix / p.Wo;
-    int oy = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
+    int c = (i % C4) * 4;
+    int pix = i / C4;
+    int ox = pix % p.Wo;
+    int t = pix / p.Wo;
+    int oy = t % p.Ho;
+    int n = t / p.Ho;
     const long long sbase = (long long)n * p.H * p.W * p.in_ld + p.in_coff + c;
 #define SRC4(off) ld4(p.in, p.in_fmt, p.in_plane, sbase + (off))
     float4 v;
@@ -283,7 +431,7 @@ __global__ void __launch_bounds__(256) elementwise4_kernel(const EwK p) {
         }
     }
 #undef SRC4
-    st4(p.out, p.out_fmt, p.out_plane, pix * p.out_ld + p.out_coff + c, v);
+    st4(p.out, p.out_fmt, p.out_plane, (long long)pix * p.out_ld + p.out_coff + c, v);
 }
 
 static bool ew_vec_ok(const EwK& k) {
@@ -372,12 +520,12 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
     for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i / 16][i % 16] = p.w[(i % 16) * 27 + i / 16];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.f);
     __syncthreads();
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
-    int ox = (int)(i % p.Wo);
-    long long t = i / p.Wo;
-    int oy = (int)(t % p.Ho);
-    int n = (int)(t / p.Ho);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
+    int ox = i % p.Wo;
+    int t = i / p.Wo;
+    int oy = t % p.Ho;
+    int n = t / p.Ho;
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = 0.f;
@@ -406,7 +554,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
             }
         }
     }
-    const long long o = i * p.out_ld + p.out_coff;
+    const long long o = (long long)i * p.out_ld + p.out_coff;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         float4 v;
@@ -442,28 +590,38 @@ int launch_stem_conv(const ConvArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gap_kernel(const void* in, int in_fmt, long long in_plane, int in_ld, int in_coff,
                                                   int HW, int C, float* out, int out_ld, int out_coff) {
-    __shared__ float part[8][33];
+    // block = 32 channel quads x 8 pixel lanes; fixed summation order (deterministic)
+    __shared__ float4 part[8][33];
     int n = blockIdx.y;
-    int c = blockIdx.x * 32 + threadIdx.x;
-    float s = 0.f;
+    int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) {
         const long long sb = (long long)n * HW * in_ld + in_coff + c;
-        for (int p = threadIdx.y; p < HW; p += 8) s += ld1(in, in_fmt, in_plane, sb + (long long)p * in_ld);
+        for (int p = threadIdx.y; p < HW; p += 8) {
+            const float4 v = ld4(in, in_fmt, in_plane, sb + (long long)p * in_ld);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
     }
     part[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
-        float t = 0.f;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) t += part[j][threadIdx.x];
-        out[(long long)n * out_ld + out_coff + c] = t / (float)HW;
+        for (int j = 0; j < 8; ++j) {
+            const float4 v = part[j][threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        const float inv = (float)HW;
+        *reinterpret_cast<float4*>(out + (long long)n * out_ld + out_coff + c) =
+            make_float4(t.x / inv, t.y / inv, t.z / inv, t.w / inv);
     }
 }
 
 int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s) {
     SKPS_CHECK(in.C == out.C && out.H == 1 && out.W == 1 && in.c_stride == 1 && out.c_stride == 1, "gap: shape");
-    dim3 grid((in.C + 31) / 32, batch), block(32, 8);
     SKPS_CHECK(out.fmt == DT_F32, "gap: output must be float32");
+    SKPS_CHECK(((in.C | in.ld | in.c_off | out.ld | out.c_off) & 3) == 0, "gap: channels/offsets must be multiples of 4");
+    dim3 grid((in.C / 4 + 31) / 32, batch), block(32, 8);
     gap_kernel<<<grid, block, 0, s>>>(in.base, in.fmt, in.plane, in.ld, in.c_off, in.H * in.W, in.C,
                                       (float*)out.base, out.ld, out.c_off);
     SKPS_CUDA(cudaGetLastError());
@@ -482,8 +640,8 @@ struct DetK {
 };
 
 __global__ void __launch_bounds__(256) det_decode_kernel(const DetK p) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.total) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
     int row = (int)(i % p.rows);
     int n = (int)(i / p.rows);
     int si = 0, r = row;

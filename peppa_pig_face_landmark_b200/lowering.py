@@ -573,6 +573,33 @@ class _Lowerer:
         return None
 
 
+def _fuse_upsample_concat_dw(pl):
+    """Resize(linear x2) -> Concat(skip) -> depthwise 3x3 (the head of each DecoderBlock, model.py:133-196)
+    becomes one OP_UPCAT_DW that interpolates on the fly; the up-sampled tensor is never written."""
+    for d in list(pl.ops):
+        if d.type != P.OP_DWCONV or list(d.k) != [3, 3] or list(d.s) != [1, 1] or list(d.d) != [1, 1] or list(d.p) != [1, 1]:
+            continue
+        x = d.ins[0]
+        if x.c_off != 0 or x.c_stride != 1 or x.C != x.buf.C:
+            continue
+        ups = [u for u in pl.ops if u.type == P.OP_UPSAMPLE_BILINEAR2X and u.outs[0].buf is x.buf and u.outs[0].c_off == 0
+               and u.outs[0].c_stride == 1]
+        if len(ups) != 1:
+            continue
+        u = ups[0]
+        cu = u.outs[0].C
+        readers = [o for o in pl.ops if o is not d and any(v is not None and v.buf is x.buf and v.c_off < cu for v in o.ins)]
+        low = u.ins[0]
+        ok8 = all(v % 8 == 0 for v in (cu, x.C - cu, x.buf.C, low.C, low.buf.C, low.c_off,
+                                      d.outs[0].buf.C, d.outs[0].c_off))
+        if readers or low.c_stride != 1 or d.outs[0].c_stride != 1 or not ok8 or cu >= x.C:
+            continue
+        d.type = P.OP_UPCAT_DW
+        x.buf.name += ":skip-only"         # the first `cu` channels of this buffer are never written any more
+        d.ins = [low, P.View(x.buf, cu, 1, x.C - cu)]
+        pl.ops.remove(u)
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -580,6 +607,7 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     lw = _Lowerer(g, name or onnx_path, in_hw, input_u8, use_tc)
     lw.analyse()
     lw.emit()
+    _fuse_upsample_concat_dw(lw.plan)
     if not lw.plan.outputs:
         raise LoweringError("no outputs produced for %s" % onnx_path)
     return lw.plan

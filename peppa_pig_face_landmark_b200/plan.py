@@ -27,6 +27,7 @@ OP_SCSE = 9           # x*cse[n,c] + x*sse[n,h,w]
 OP_DET_DECODE = 10    # yolov5-face head decode -> (N,rows,16)
 OP_HM_DECODE = 11     # heat-map argmax + offset decode -> (N,196),(N,98)
 OP_SCALE_CH = 12      # x * gate[n,c]  (squeeze-excite applied ahead of a tensor-core conv)
+OP_UPCAT_DW = 13      # depthwise3x3(concat(bilinear_x2(low), skip)) without materialising the up-sampled tensor
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
 
