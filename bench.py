@@ -301,7 +301,7 @@ def main():
                    "l2": "inputs rotate over 4 x 50 MB sets (> 126 MB L2); activations per batch exceed L2"},
         "e2e": {"value": e2e_fps, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "ONNXEngine.run_u8 (pinned host crops in, host landmarks+scores out)"},
-        "gpu_launches": eng.launches * args.steps,
+        "gpu_launches": lib.skps_engine_launches_for_batch(eng.handle, B) * args.steps,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
     print(json.dumps(line))

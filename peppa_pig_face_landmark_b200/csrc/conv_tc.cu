@@ -178,8 +178,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
-                const int img = m_idx / p.tiles_per_img;
-                const int t = m_idx - img * p.tiles_per_img;
+                const int img_l = m_idx / p.tiles_per_img, img = img_l + p.img0;
+                const int t = m_idx - img_l * p.tiles_per_img;
                 const int tiles_x = p.W / p.bw;
                 const int y0 = (t / tiles_x) * p.bh, x0 = (t % tiles_x) * p.bw;
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -248,8 +248,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int tiles_x = p.W / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
-            const int img = m_idx / p.tiles_per_img;
-            const int t = m_idx - img * p.tiles_per_img;
+            const int img_l = m_idx / p.tiles_per_img, img = img_l + p.img0;
+            const int t = m_idx - img_l * p.tiles_per_img;
             const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
             const long long pix = ((long long)img * p.H + y) * p.W + x;
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
@@ -437,9 +437,10 @@ static int tc_launch_t(const TcLayer& L, const TcK& k, int grid, cudaStream_t st
     return 0;
 }
 
-int tc_launch(const TcLayer& L, int batch, int num_sms, cudaStream_t stream) {
+int tc_launch(const TcLayer& L, int batch, int img0, int num_sms, cudaStream_t stream) {
     TcK k = L.k;
     k.m_tiles = batch * k.tiles_per_img;
+    k.img0 = img0;
     int total = k.m_tiles * k.n_tiles;
     int grid = total < num_sms ? total : num_sms;
     const bool sp = k.out_fmt == DT_SPLIT16;
@@ -516,7 +517,7 @@ extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (tc_launch(L, N, sms, 0)) return 1;
+    if (tc_launch(L, N, 0, sms, 0)) return 1;
     SKPS_CUDA(cudaDeviceSynchronize());
     if (out_split) {
         // recombine hi+lo on the host side of the test

@@ -8,6 +8,7 @@ namespace skps {
 
 struct TcK {                     // kernel parameters
     int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
+    int img0;                    // first sample of this launch (sub-batch execution)
     int taps, kw, dil, pad, cchunks;
     int Cout, Cin, act, stages;
     float out_scale;             // exact power of two undoing the weight pre-scale
@@ -36,6 +37,6 @@ struct TcSetup {
 
 bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff);
 int tc_prepare(TcLayer& L, const TcSetup& s);
-int tc_launch(const TcLayer& L, int batch, int num_sms, cudaStream_t stream);
+int tc_launch(const TcLayer& L, int batch, int img0, int num_sms, cudaStream_t stream);
 
 }  // namespace skps

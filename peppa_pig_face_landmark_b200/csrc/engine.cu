@@ -46,6 +46,8 @@ struct skps_engine {
     bool use_graph = true;
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
+    struct Segment { int first, end, chunk; };
+    std::vector<Segment> segments;        // ops [first,end) run `chunk` samples at a time (L2 residency)
 };
 
 static size_t buf_elems(const BufDesc& b) { return (size_t)b.C * b.H * b.W; }
@@ -61,12 +63,16 @@ static float half_bits_to_float(uint16_t h) {
     float f; memcpy(&f, &bits, 4); return f;
 }
 
-static TView resolve(const skps_engine* e, const View& v) {
+static TView resolve(const skps_engine* e, const View& v, int b0 = 0) {
     TView t;
     memset(&t, 0, sizeof(t));
     if (v.buf < 0) return t;
     const BufDesc& b = e->bufs[v.buf];
-    t.base = (v.buf == e->input_buf && e->f32_mode) ? (void*)e->d_in_f32 : e->dbuf[v.buf];
+    const bool f32in = (v.buf == e->input_buf && e->f32_mode);
+    t.base = f32in ? (void*)e->d_in_f32 : e->dbuf[v.buf];
+    // sub-batch offset: samples b0.. (SPLIT16 planes are 2 bytes per element each)
+    const size_t esz = f32in ? 4 : (b.dtype == DT_U8 ? 1 : (b.dtype == DT_SPLIT16 ? 2 : 4));
+    t.base = (char*)t.base + (size_t)b0 * b.C * b.H * b.W * esz;
     t.ld = b.C;
     t.c_off = v.c_off; t.c_stride = v.c_stride; t.C = v.C; t.H = b.H; t.W = b.W;
     t.sample = (long long)b.C * b.H * b.W;
@@ -75,19 +81,20 @@ static TView resolve(const skps_engine* e, const View& v) {
     return t;
 }
 
-static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int last = -1) {
+// Enqueue ops [first,last) for samples [b0, b0+batch).
+static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int last = -1, int b0 = 0) {
     const size_t end = last < 0 ? e->ops.size() : (size_t)last;
     for (size_t i = (size_t)first; i < end; ++i) {
         const OpDesc& op = e->ops[i];
-        TView in0 = resolve(e, op.in[0]), in1 = resolve(e, op.in[1]), in2 = resolve(e, op.in[2]);
-        TView out0 = resolve(e, op.out[0]), out1 = resolve(e, op.out[1]);
+        TView in0 = resolve(e, op.in[0], b0), in1 = resolve(e, op.in[1], b0), in2 = resolve(e, op.in[2], b0);
+        TView out0 = resolve(e, op.out[0], b0), out1 = resolve(e, op.out[1], b0);
         const float* w = op.w_off >= 0 ? e->d_weights + op.w_off : nullptr;
         const float* b = op.b_off >= 0 ? e->d_weights + op.b_off : nullptr;
         int rc = 0;
         switch (op.type) {
             case OP_CONV: {
                 if (op.flags & FLAG_TC) {
-                    rc = tc_launch(e->tc[i], batch, e->num_sms, s);
+                    rc = tc_launch(e->tc[i], batch, b0, e->num_sms, s);
                     break;
                 }
                 ConvArgs a;
@@ -133,6 +140,17 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
     return 0;
 }
 
+// Whole forward: every segment sweeps the batch in L2-sized chunks.
+static int run_forward(skps_engine* e, int batch, cudaStream_t s) {
+    for (const auto& sg : e->segments) {
+        for (int b0 = 0; b0 < batch; b0 += sg.chunk) {
+            int nb = batch - b0 < sg.chunk ? batch - b0 : sg.chunk;
+            if (run_ops(e, nb, s, sg.first, sg.end, b0)) return 1;
+        }
+    }
+    return 0;
+}
+
 extern "C" SKPS_API const char* skps_last_error(void) { return get_error(); }
 extern "C" SKPS_API int skps_version(void) { return 1; }
 
@@ -141,7 +159,8 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
     SKPS_CHECK(words && weights && out && n_words >= 8 && max_batch > 0, "engine_create: bad arguments");
     SKPS_CHECK(words[0] == PLAN_MAGIC && words[1] == 1, "engine_create: bad plan header");
     int n_bufs = words[2], n_ops = words[3];
-    SKPS_CHECK(n_words == (size_t)8 + 4 * (size_t)n_bufs + OP_WORDS * (size_t)n_ops, "engine_create: plan size mismatch");
+    const size_t body = (size_t)8 + 4 * (size_t)n_bufs + OP_WORDS * (size_t)n_ops;
+    SKPS_CHECK(n_words > body && n_words == body + 1 + 3 * (size_t)words[body], "engine_create: plan size mismatch");
     SKPS_CUDA(cudaSetDevice(device));
     skps_engine* e = new skps_engine();
     e->device = device;
@@ -152,6 +171,10 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
     for (int i = 0; i < n_bufs; ++i, p += 4) e->bufs.push_back(BufDesc{p[0], p[1], p[2], p[3]});
     e->ops.resize(n_ops);
     memcpy(e->ops.data(), p, sizeof(OpDesc) * n_ops);
+    {
+        const int32_t* t = words + body;
+        for (int i = 0; i < t[0]; ++i) e->segments.push_back({t[1 + 3 * i], t[2 + 3 * i], t[3 + 3 * i]});
+    }
     e->h_weights.assign(weights, weights + n_floats);
     e->n_weights = n_floats;
     e->launches = n_ops;
@@ -271,6 +294,12 @@ extern "C" SKPS_API int skps_engine_read_buffer(skps_engine* e, int buf, int bat
     return 0;
 }
 extern "C" SKPS_API int skps_engine_launches_per_forward(const skps_engine* e) { return e ? e->launches : 0; }
+extern "C" SKPS_API int skps_engine_launches_for_batch(const skps_engine* e, int batch) {
+    if (!e) return 0;
+    long long n = 0;
+    for (const auto& sg : e->segments) n += (long long)(sg.end - sg.first) * ((batch + sg.chunk - 1) / sg.chunk);
+    return (int)n;
+}
 
 extern "C" SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int batch, void* stream) {
     SKPS_CHECK(e && op_index >= 0 && op_index < (int)e->ops.size(), "run_op: bad op index");
@@ -281,16 +310,16 @@ extern "C" SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int bat
 
 // Enqueue the op sequence (through a cached CUDA graph when possible).
 static int enqueue(skps_engine* e, int batch, cudaStream_t s) {
-    if (!e->use_graph || s == nullptr) return run_ops(e, batch, s);   // the legacy default stream cannot be captured
+    if (!e->use_graph || s == nullptr) return run_forward(e, batch, s);   // the legacy default stream cannot be captured
     const int key = batch * 2 + (e->f32_mode ? 1 : 0);
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
         cudaStreamCaptureStatus st;
         SKPS_CUDA(cudaStreamIsCapturing(s, &st));
-        if (st != cudaStreamCaptureStatusNone) return run_ops(e, batch, s);   // already inside a capture
+        if (st != cudaStreamCaptureStatusNone) return run_forward(e, batch, s);   // already inside a capture
         cudaGraph_t g = nullptr;
         SKPS_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        int rc = run_ops(e, batch, s);
+        int rc = run_forward(e, batch, s);
         cudaError_t ce = cudaStreamEndCapture(s, &g);
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         SKPS_CUDA(ce);

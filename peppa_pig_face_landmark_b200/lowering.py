@@ -14,6 +14,8 @@ plan.py.  Patterns handled:
   yolov5-face Detect tail (face_detector graph nodes 502-820)                       -> OP_DET_DECODE
   heat-map arg-max tail (kps graph nodes 201-410; model.py:511-554)                 -> OP_HM_DECODE
 """
+import os
+
 import numpy as np
 
 from . import plan as P
@@ -608,6 +610,9 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     lw.analyse()
     lw.emit()
     _fuse_upsample_concat_dw(lw.plan)
+    chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
+    if chunk_env not in ("0", ""):
+        lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)
     if not lw.plan.outputs:
         raise LoweringError("no outputs produced for %s" % onnx_path)
     return lw.plan

@@ -43,6 +43,7 @@ SIGNATURES = {
     "skps_engine_buffer_dims": (C.c_int, [c_vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p]),
     "skps_engine_read_buffer": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "skps_engine_launches_per_forward": (C.c_int, [c_vp]),
+    "skps_engine_launches_for_batch": (C.c_int, [c_vp, C.c_int]),
     "skps_engine_run_op": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),
     "skps_debug_conv_tc": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_vp, C.c_int, c_vp]),

@@ -49,7 +49,10 @@ def test_plan_serialisation_layout():
     plan = lowering.lower(os.path.join(PRE, "kps_student.onnx"), (256, 256))
     words, blob = plan.serialize()
     assert words[0] == 0x534B5053 and words[2] == len(plan.bufs) and words[3] == len(plan.ops)
-    assert words.size == 8 + 4 * len(plan.bufs) + P.OP_WORDS * len(plan.ops)
+    body = 8 + 4 * len(plan.bufs) + P.OP_WORDS * len(plan.ops)
+    assert words.size == body + 1 + 3 * words[body]          # trailer: L2 chunking segments
+    segs = words[body + 1:].reshape(-1, 3)
+    assert segs[0, 0] == 0 and segs[-1, 1] == len(plan.ops) and (segs[1:, 0] == segs[:-1, 1]).all()
     assert blob.dtype == np.float32 and all(op.w_off % 4 == 0 for op in plan.ops if op.w_off >= 0)
 
 
