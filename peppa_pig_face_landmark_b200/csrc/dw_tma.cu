@@ -1,0 +1,389 @@
+// Depthwise convolution with TMA-staged input tiles (sm_100a).
+//
+// The register-gather depthwise kernel (ops_misc.cu) is latency bound on B200: each thread has only a
+// handful of 8-byte loads in flight.  Here one CTA owns an 8x16 output tile x CB channels; a single
+// thread issues one 4-D TMA box per float16 plane (or one float32 box) covering the tile plus its
+// halo, with the convolution's zero padding coming from TMA out-of-bounds fill, and everything else
+// is computed out of shared memory.  Several CTAs per SM keep ~100 KB of loads in flight per SM.
+//
+// Covers the landmark network's depthwise layers (kps_student.onnx conv_dw nodes; 3x3 and 5x5,
+// stride 1/2, dilation 1/2) and the detector's (3x3, stride 1/2).  Same arithmetic order as
+// dwconv_kernel: bias first, then taps in (ky,kx) order with fmaf.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.h"
+#include "dw_tma.h"
+
+namespace skps {
+
+__device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+constexpr int TH = 8, TW = 16;          // output tile
+constexpr int DW_THREADS = 256;
+
+template <int K, int S, int D, bool SPLIT_IN>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const DwTmaK p) {
+    constexpr int CB = SPLIT_IN ? 64 : 32;                 // channels per CTA: 128-byte pixel rows in smem
+    constexpr int CG = CB / 4;                             // 4-channel groups
+    constexpr int PGS = DW_THREADS / CG;                   // pixel groups
+    constexpr int PX = TH * TW / PGS;                      // consecutive output pixels (along x) per thread
+    constexpr int IH = (TH - 1) * S + (K - 1) * D + 1, IW = (TW - 1) * S + (K - 1) * D + 1;
+    constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
+    constexpr int ROW_BYTES = 128;
+    constexpr int PLANE_BYTES = IH * IW * ROW_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.Wo + TW - 1) / TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int chunk = blockIdx.y;
+    const int n = blockIdx.z + p.img0;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const uint32_t sbase = (dsmem_u32(smem) + 127u) & ~127u;
+    const uint32_t bar_a = dsmem_u32(&bar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                     "r"((uint32_t)(SPLIT_IN ? 2 * PLANE_BYTES : PLANE_BYTES)) : "memory");
+        const int cx = ox0 * S - p.pad, cy = oy0 * S - p.pad, cc = chunk * CB;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(sbase), "l"(&tm_hi), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
+        if (SPLIT_IN)
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(sbase + PLANE_BYTES), "l"(&tm_lo), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
+    }
+    // thread -> (4-channel group, row, x segment)
+    const int cg = tid % CG, pg = tid / CG;
+    constexpr int SEGS = TW / PX;
+    const int row = pg / SEGS, xs = (pg % SEGS) * PX;
+    const int c = chunk * CB + cg * 4;
+    const bool c_ok = c < p.C;
+    float4 acc[PX];
+    {
+        const float4 b = c_ok ? *reinterpret_cast<const float4*>(p.bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < PX; ++q) acc[q] = b;
+    }
+    __syncthreads();        // barrier init visible to all waiters
+    {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "DW_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra DW_DONE;\n\t"
+            "bra DW_WAIT;\n\t"
+            "DW_DONE:\n\t"
+            "}\n" ::"r"(bar_a) : "memory");
+    }
+    const uint8_t* tile = smem + (sbase - dsmem_u32(smem));
+    if (c_ok) {
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            float4 in[SPAN];
+            const int iy = row * S + ky * D;
+#pragma unroll
+            for (int j = 0; j < SPAN; ++j) {
+                bool used = false;
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == j);
+                if (!used) continue;
+                const int off = (iy * IW + xs * S + j) * ROW_BYTES;
+                if (SPLIT_IN) {
+                    const uint2 a = *reinterpret_cast<const uint2*>(tile + off + cg * 8);
+                    const uint2 b = *reinterpret_cast<const uint2*>(tile + PLANE_BYTES + off + cg * 8);
+                    const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+                    const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+                    const float2 a01 = __half22float2(a2[0]), a23 = __half22float2(a2[1]);
+                    const float2 b01 = __half22float2(b2[0]), b23 = __half22float2(b2[1]);
+                    in[j] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+                } else {
+                    in[j] = *reinterpret_cast<const float4*>(tile + off + cg * 16);
+                }
+            }
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const float4 w = *reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.w_ld + c);
+#pragma unroll
+                for (int q = 0; q < PX; ++q) {
+                    const float4 v = in[q * S + kx * D];
+                    acc[q].x = fmaf(v.x, w.x, acc[q].x);
+                    acc[q].y = fmaf(v.y, w.y, acc[q].y);
+                    acc[q].z = fmaf(v.z, w.z, acc[q].z);
+                    acc[q].w = fmaf(v.w, w.w, acc[q].w);
+                }
+            }
+        }
+        const int oy = oy0 + row;
+        if (oy < p.Ho) {
+#pragma unroll
+            for (int q = 0; q < PX; ++q) {
+                const int ox = ox0 + xs + q;
+                if (ox >= p.Wo) break;
+                float4 a = acc[q];
+                a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
+                a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+                st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Up-sampled channels of a DecoderBlock head: out[:, :Cu] = depthwise3x3(bilinear_x2(low)) with the
+// 2x interpolation done out of a TMA-staged low-res tile (float32, 32 channels per CTA).
+// One thread = a 2x2 block of output pixels x 4 channels (fixed .25/.75 blend weights).
+// ------------------------------------------------------------------------------------------
+constexpr int LH = TH / 2 + 2, LW = TW / 2 + 2;      // low-res tile incl. halo
+
+__global__ void __launch_bounds__(DW_THREADS)
+upcat_tma_kernel(const __grid_constant__ CUtensorMap tm_low, const DwTmaK p, const int Hl, const int Wl) {
+    constexpr int CB = 32, CG = CB / 4;
+    constexpr int BYTES = LH * LW * 128;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.Wo + TW - 1) / TW;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int chunk = blockIdx.y;
+    const int n = blockIdx.z + p.img0;
+    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int ly0 = oy0 / 2 - 1, lx0 = ox0 / 2 - 1;          // low-res origin of the tile (may be -1)
+    const uint32_t sbase = (dsmem_u32(smem) + 127u) & ~127u;
+    const uint32_t bar_a = dsmem_u32(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(sbase), "l"(&tm_low), "r"(bar_a), "r"(chunk * CB), "r"(lx0), "r"(ly0), "r"(n) : "memory");
+    }
+    const int cg = tid % CG, pg = tid / CG;                  // 32 pixel groups = 4 x 8 blocks of 2x2
+    const int byl = pg / (TW / 2), bxl = pg % (TW / 2);
+    const int c = chunk * CB + cg * 4;
+    const bool c_ok = c < p.C;
+    float4 w[9];
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c_ok) {
+        bias = *reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(p.w + k * p.w_ld + c);
+    }
+    __syncthreads();
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "UP_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra UP_DONE;\n\t"
+        "bra UP_WAIT;\n\t"
+        "UP_DONE:\n\t"
+        "}\n" ::"r"(bar_a) : "memory");
+    if (!c_ok) return;
+    const uint8_t* tile = smem + (sbase - dsmem_u32(smem));
+    const int oyb = oy0 + 2 * byl, oxb = ox0 + 2 * bxl;     // top-left output pixel of this thread's 2x2 block
+    if (oyb >= p.Ho || oxb >= p.Wo) return;
+    const int by = oyb >> 1, bx = oxb >> 1;                  // low-res pixel under the block
+    // columns/rows outside the high-res image are the depthwise conv's zero padding
+    const float vx0 = oxb > 0 ? 1.f : 0.f, vx3 = oxb + 2 < p.Wo ? 1.f : 0.f;
+    const float vy0 = oyb > 0 ? 1.f : 0.f, vy3 = oyb + 2 < p.Ho ? 1.f : 0.f;
+    float4 Hh[3][4];
+#define BLEND(dst, a, b, wa, wb, m)                                                   \
+    dst.x = (m) * ((wa) * a.x + (wb) * b.x); dst.y = (m) * ((wa) * a.y + (wb) * b.y); \
+    dst.z = (m) * ((wa) * a.z + (wb) * b.z); dst.w = (m) * ((wa) * a.w + (wb) * b.w);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int ly = min(max(by - 1 + r, 0), Hl - 1) - ly0;          // edge-replicated, in tile coordinates
+        float4 L[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const int lx = min(max(bx - 1 + q, 0), Wl - 1) - lx0;
+            L[q] = *reinterpret_cast<const float4*>(tile + (ly * LW + lx) * 128 + cg * 16);
+        }
+        BLEND(Hh[r][0], L[0], L[1], 0.75f, 0.25f, vx0)
+        BLEND(Hh[r][1], L[0], L[1], 0.25f, 0.75f, 1.f)
+        BLEND(Hh[r][2], L[1], L[2], 0.75f, 0.25f, 1.f)
+        BLEND(Hh[r][3], L[1], L[2], 0.25f, 0.75f, vx3)
+    }
+    float4 acc[2][2] = {{bias, bias}, {bias, bias}};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int a = r >> 1;
+        const float wa = (r & 1) ? 0.25f : 0.75f, wb = 1.f - wa;
+        const float m = r == 0 ? vy0 : (r == 3 ? vy3 : 1.f);
+        float4 U[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { BLEND(U[j], Hh[a][j], Hh[a + 1][j], wa, wb, m) }
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+            const int ky = r - oy;
+            if (ky < 0 || ky > 2) continue;
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 v = U[ox + kx], ww = w[ky * 3 + kx];
+                    acc[oy][ox].x = fmaf(v.x, ww.x, acc[oy][ox].x);
+                    acc[oy][ox].y = fmaf(v.y, ww.y, acc[oy][ox].y);
+                    acc[oy][ox].z = fmaf(v.z, ww.z, acc[oy][ox].z);
+                    acc[oy][ox].w = fmaf(v.w, ww.w, acc[oy][ox].w);
+                }
+        }
+    }
+#undef BLEND
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 2; ++ox) {
+            float4 v = acc[oy][ox];
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+            st4(p.out, p.out_fmt, p.out_plane,
+                (((long long)n * p.Ho + oyb + oy) * p.Wo + oxb + ox) * p.out_ld + p.out_coff + c, v);
+        }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn dw_get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static bool variant_ok(int k, int s, int d) {
+    return (k == 3 && s == 1 && d == 1) || (k == 3 && s == 2 && d == 1) || (k == 5 && s == 1 && d == 1) ||
+           (k == 5 && s == 2 && d == 1) || (k == 5 && s == 1 && d == 2);
+}
+
+bool dw_tma_supported(const TView& in, const TView& out, int k, int s, int d, int pad) {
+    if (!variant_ok(k, s, d) || pad != d * (k - 1) / 2) return false;
+    if (in.fmt != DT_F32 && in.fmt != DT_SPLIT16) return false;
+    if (in.c_stride != 1 || out.c_stride != 1 || in.C != out.C) return false;
+    if ((in.C | in.ld | in.c_off | out.ld | out.c_off) & 7) return false;
+    return true;
+}
+
+int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float* w, const float* bias, int k, int s,
+                   int d, int pad, int act, int max_batch) {
+    EncodeTiledFn enc = dw_get_encode();
+    SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+    SKPS_CHECK(dw_tma_supported(in, out, k, s, d, pad), "dw_tma: unsupported layer");
+    const bool split = in.fmt == DT_SPLIT16;
+    const int CB = split ? 64 : 32, esz = split ? 2 : 4;
+    const int IH = (TH - 1) * s + (k - 1) * d + 1, IW = (TW - 1) * s + (k - 1) * d + 1;
+    for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
+        cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)max_batch};
+        cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.W * in.ld * esz, (cuuint64_t)in.H * in.W * in.ld * esz};
+        cuuint32_t box[4] = {(cuuint32_t)CB, (cuuint32_t)IW, (cuuint32_t)IH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        char* base = (char*)in.base + (size_t)in.c_off * esz + (plane ? (size_t)in.plane * 2 : 0);
+        CUresult r = enc(plane ? &L.lo : &L.hi, split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dw) failed: %d", (int)r);
+    }
+    if (!split) L.lo = L.hi;
+    DwTmaK& kk = L.k;
+    kk.C = in.C; kk.Ho = out.H; kk.Wo = out.W; kk.pad = pad; kk.act = act; kk.img0 = 0;
+    kk.w = w; kk.bias = bias; kk.w_ld = in.C;
+    kk.out = out.base; kk.out_fmt = out.fmt; kk.out_plane = out.plane; kk.out_ld = out.ld; kk.out_coff = out.c_off;
+    L.k_size = k; L.stride = s; L.dil = d; L.split = split ? 1 : 0;
+    L.chunks = (in.C + CB - 1) / CB;
+    L.smem_bytes = IH * IW * 128 * (split ? 2 : 1) + 128;
+    return 0;
+}
+
+template <int K, int S, int D, bool SPLIT>
+static int launch_variant(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKPS_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dw_tma_kernel<K, S, D, SPLIT><<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.hi, L.lo, k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream) {
+    DwTmaK k = L.k;
+    k.img0 = img0;
+    dim3 grid(((k.Ho + TH - 1) / TH) * ((k.Wo + TW - 1) / TW), L.chunks, batch);
+#define DW_CASE(K_, S_, D_)                                                                              \
+    if (L.k_size == K_ && L.stride == S_ && L.dil == D_)                                                 \
+        return L.split ? launch_variant<K_, S_, D_, true>(L, k, grid, stream)                            \
+                       : launch_variant<K_, S_, D_, false>(L, k, grid, stream);
+    DW_CASE(3, 1, 1) DW_CASE(3, 2, 1) DW_CASE(5, 1, 1) DW_CASE(5, 2, 1) DW_CASE(5, 1, 2)
+#undef DW_CASE
+    set_error("dw_tma: variant k=%d s=%d d=%d not instantiated", L.k_size, L.stride, L.dil);
+    return 1;
+}
+
+
+bool upcat_tma_supported(const TView& low, const TView& skip, const TView& out) {
+    if (low.fmt != DT_F32 || low.c_stride != 1 || out.c_stride != 1) return false;
+    if ((low.C | low.ld | low.c_off | out.ld | out.c_off) & 7) return false;
+    if (out.H != 2 * low.H || out.W != 2 * low.W || (out.H & 1) || (out.W & 1)) return false;
+    TView o2 = out;
+    o2.c_off += low.C; o2.C = skip.C;
+    return dw_tma_supported(skip, o2, 3, 1, 1, 1);
+}
+
+int upcat_tma_prepare(UpcatTmaLayer& L, const TView& low, const TView& skip, const TView& out, const float* w,
+                      const float* bias, int act, int max_batch) {
+    EncodeTiledFn enc = dw_get_encode();
+    SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
+    SKPS_CHECK(upcat_tma_supported(low, skip, out), "upcat_tma: unsupported layer");
+    cuuint64_t dims[4] = {(cuuint64_t)low.C, (cuuint64_t)low.W, (cuuint64_t)low.H, (cuuint64_t)max_batch};
+    cuuint64_t strides[3] = {(cuuint64_t)low.ld * 4, (cuuint64_t)low.W * low.ld * 4, (cuuint64_t)low.H * low.W * low.ld * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)LW, (cuuint32_t)LH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&L.low, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (char*)low.base + (size_t)low.c_off * 4, dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(upcat) failed: %d", (int)r);
+    const int Ctot = low.C + skip.C;
+    DwTmaK& k = L.k;
+    k.C = low.C; k.Ho = out.H; k.Wo = out.W; k.pad = 1; k.act = act; k.img0 = 0; k.w_ld = Ctot;
+    k.w = w; k.bias = bias;
+    k.out = out.base; k.out_fmt = out.fmt; k.out_plane = out.plane; k.out_ld = out.ld; k.out_coff = out.c_off;
+    L.Hl = low.H; L.Wl = low.W;
+    L.chunks = (low.C + 31) / 32;
+    L.smem_bytes = LH * LW * 128 + 128;
+    // skip channels: an ordinary depthwise layer over the channel slice [Cu, Ctot)
+    TView o2 = out;
+    o2.c_off += low.C; o2.C = skip.C;
+    if (dw_tma_prepare(L.skip, skip, o2, w + low.C, bias + low.C, 3, 1, 1, 1, act, max_batch)) return 1;
+    L.skip.k.w_ld = Ctot;
+    return 0;
+}
+
+int upcat_tma_launch(const UpcatTmaLayer& L, int batch, int img0, cudaStream_t stream) {
+    DwTmaK k = L.k;
+    k.img0 = img0;
+    dim3 grid(((k.Ho + TH - 1) / TH) * ((k.Wo + TW - 1) / TW), L.chunks, batch);
+    upcat_tma_kernel<<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.low, k, L.Hl, L.Wl);
+    SKPS_CUDA(cudaGetLastError());
+    return dw_tma_launch(L.skip, batch, img0, stream);
+}
+
+}  // namespace skps

@@ -4,6 +4,7 @@
 // (sized for max_batch at creation: no allocation on the forward path); the op sequence for a
 // given batch size is captured once into a CUDA graph and replayed.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -12,6 +13,7 @@
 #include "../../include/skps_b200.h"
 #include "common.h"
 #include "conv_tc.h"
+#include "dw_tma.h"
 
 namespace skps {
 
@@ -46,6 +48,9 @@ struct skps_engine {
     bool use_graph = true;
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
+    std::vector<DwTmaLayer> dwt;          // per op; TMA-staged depthwise layers (valid flag)
+    std::vector<UpcatTmaLayer> upt;       // per op; TMA-staged fused upsample+concat+depthwise
+    bool use_dw_tma = true;
     struct Segment { int first, end, chunk; };
     std::vector<Segment> segments;        // ops [first,end) run `chunk` samples at a time (L2 residency)
 };
@@ -106,6 +111,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 break;
             }
             case OP_DWCONV: {
+                if (e->dwt[i].valid) {
+                    rc = dw_tma_launch(e->dwt[i], batch, b0, s);
+                    break;
+                }
                 DwArgs a;
                 a.in = in0; a.out = out0; a.w = w; a.bias = b;
                 a.kh = op.kh; a.kw = op.kw; a.sh = op.sh; a.sw = op.sw; a.ph = op.ph; a.pw = op.pw;
@@ -121,7 +130,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
             case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
-            case OP_UPCAT_DW: rc = launch_upcat_dw(in0, in1, out0, w, b, op.act, batch, s); break;
+            case OP_UPCAT_DW:
+                rc = e->upt[i].valid ? upcat_tma_launch(e->upt[i], batch, b0, s)
+                                     : launch_upcat_dw(in0, in1, out0, w, b, op.act, batch, s);
+                break;
             case OP_DET_DECODE: {
                 TView heads[3] = {in0, in1, in2};
                 rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);
@@ -231,6 +243,40 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
             set_error("op %d: %s", i, tmp);
             return fail("tc");
         }
+    }
+    // depthwise layers: TMA descriptors over the input views
+    e->dwt.resize(n_ops);
+    {
+        const char* env = getenv("SKPS_DW_TMA");
+        e->use_dw_tma = !(env && env[0] == '0');
+    }
+    e->upt.resize(n_ops);
+    for (int i = 0; i < n_ops && e->use_dw_tma; ++i) {
+        const OpDesc& op = e->ops[i];
+        if (op.type == OP_UPCAT_DW) {
+            TView low = resolve(e, op.in[0]), skip = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
+            if (!upcat_tma_supported(low, skip, out0)) continue;
+            if (upcat_tma_prepare(e->upt[i], low, skip, out0, e->d_weights + op.w_off, e->d_weights + op.b_off, op.act,
+                                  max_batch)) {
+                char tmp[900];
+                snprintf(tmp, sizeof(tmp), "%s", get_error());
+                set_error("op %d: %s", i, tmp);
+                return fail("upcat_tma");
+            }
+            e->upt[i].valid = true;
+            continue;
+        }
+        if (op.type != OP_DWCONV || op.kh != op.kw || op.sh != op.sw || op.dh != op.dw || op.ph != op.pw) continue;
+        TView in0 = resolve(e, op.in[0]), out0 = resolve(e, op.out[0]);
+        if (!dw_tma_supported(in0, out0, op.kh, op.sh, op.dh, op.ph)) continue;
+        if (dw_tma_prepare(e->dwt[i], in0, out0, e->d_weights + op.w_off, e->d_weights + op.b_off, op.kh, op.sh, op.dh,
+                           op.ph, op.act, max_batch)) {
+            char tmp[900];
+            snprintf(tmp, sizeof(tmp), "%s", get_error());
+            set_error("op %d: %s", i, tmp);
+            return fail("dw_tma");
+        }
+        e->dwt[i].valid = true;
     }
     *out = e;
     return 0;

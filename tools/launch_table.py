@@ -9,9 +9,14 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 lines = [l for l in open(path) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
 pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/kps_student.onnx'), (256, 256))
-assert len(rows) == len(pl.ops), (len(rows), len(pl.ops))
+ops = []
+for op in pl.ops:
+    ops.append(op)
+    if op.type == P.OP_UPCAT_DW and len(rows) != len(pl.ops):
+        ops.append(op)          # TMA variant = up-sampled part + skip part, two launches
+assert len(rows) == len(ops), (len(rows), len(ops))
 out, tot, d = [], 0.0, defaultdict(float)
-for i, (row, op) in enumerate(zip(rows, pl.ops)):
+for i, (row, op) in enumerate(zip(rows, ops)):
     t = float(row['Metric Value']) / 1e3
     tot += t
     o = op.outs[0]
