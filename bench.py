@@ -55,6 +55,16 @@ def host_cores():
     return n
 
 
+def shard_frames(items, rank, world):
+    """Frame-level round-robin sharding across ranks: no collective on the data path."""
+    return list(items[rank::world])
+
+
+def whole_job_rate(world, per_rank_units_per_step, steps, seconds):
+    """Weak scaling: every rank processes the same per-GPU batch; time is the max over ranks."""
+    return world * per_rank_units_per_step * steps / seconds
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -221,7 +231,7 @@ def main():
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    faces_per_s = world * B * args.steps / (ms * 1e-3)
+    faces_per_s = whole_job_rate(world, B, args.steps, ms * 1e-3)
     log("device-resident: %.1f faces/s (%.3f ms/step)" % (faces_per_s, ms / args.steps))
 
     # ---- end to end through the operator call with host buffers (pinned), H2D + D2H inside the timed region

@@ -1,0 +1,40 @@
+"""N>1 host logic on CPU (gloo, world size 2): the bench's sharding is "same per-GPU batch on every rank, no
+collective on the data path, max-over-ranks time, whole-job throughput = world * batch * steps / time"."""
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+WORKER = textwrap.dedent('''
+    import os, sys, json
+    import torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from bench import shard_frames, whole_job_rate
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = shard_frames(list(range(10)), rank, world)          # frame-level round robin (SURVEY 8e)
+    allf = [None] * world
+    dist.all_gather_object(allf, mine)
+    t = torch.tensor([1.0 + rank])                              # rank 1 is slower
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"frames": allf, "t": float(t.item()), "rate": whole_job_rate(world, 256, 10, float(t.item()))}))
+    dist.destroy_process_group()
+''') % ROOT
+
+
+def test_gloo_world2_sharding_and_timing(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["frames"] == [[0, 2, 4, 6, 8], [1, 3, 5, 7, 9]]
+    assert d["t"] == 2.0                                         # max over ranks
+    assert d["rate"] == 2 * 256 * 10 / 2.0
