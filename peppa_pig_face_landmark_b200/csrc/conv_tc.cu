@@ -139,7 +139,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * TC_BK * 2;
-    const uint32_t stage_bytes = 2u * A_TILE_BYTES + 2u * b_tile_bytes;
+    // stage = [A0_hi][A0_lo]([A1_hi][A1_lo])[B_hi][B_lo]: with mt = 2 two pixel tiles share one weight tile
+    const uint32_t a_bytes = (uint32_t)p.mt * 2u * A_TILE_BYTES;
+    const uint32_t stage_bytes = a_bytes + 2u * b_tile_bytes;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
@@ -168,7 +170,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int m_groups = (p.m_tiles + p.mt - 1) / p.mt;
+    const int total_tiles = m_groups * p.n_tiles;          // work items: (group of mt pixel tiles) x N tile
     const int kblocks = p.taps * p.cchunks;
 
     if (warp == 0) {
@@ -176,24 +179,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const int tiles_x = p.W / p.bw;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
-                const int img_l = m_idx / p.tiles_per_img, img = img_l + p.img0;
-                const int t = m_idx - img_l * p.tiles_per_img;
-                const int tiles_x = p.W / p.bw;
-                const int y0 = (t / tiles_x) * p.bh, x0 = (t % tiles_x) * p.bw;
+                const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
+                int img[2], y0[2], x0[2];
+                for (int u = 0; u < p.mt; ++u) {
+                    const int m_idx = min(g_idx * p.mt + u, p.m_tiles - 1);     // odd tail: reload the last tile, result unused
+                    const int img_l = m_idx / p.tiles_per_img;
+                    const int t = m_idx - img_l * p.tiles_per_img;
+                    img[u] = img_l + p.img0;
+                    y0[u] = (t / tiles_x) * p.bh;
+                    x0[u] = (t % tiles_x) * p.bw;
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     mbar_expect_tx(fb, stage_bytes);
                     const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
-                    const int cx = x0 + kx * p.dil - p.pad, cy = y0 + ky * p.dil - p.pad;
                     const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
-                    tma_load_4d(sa, &tmA_hi, fb, cc * TC_BK, cx, cy, img);
-                    tma_load_4d(sa + A_TILE_BYTES, &tmA_lo, fb, cc * TC_BK, cx, cy, img);
-                    tma_load_2d(sa + 2 * A_TILE_BYTES, &tmB_hi, fb, kb * TC_BK, n_idx * p.n_tile);
-                    tma_load_2d(sa + 2 * A_TILE_BYTES + b_tile_bytes, &tmB_lo, fb, kb * TC_BK, n_idx * p.n_tile);
+                    for (int u = 0; u < p.mt; ++u) {
+                        const int cx = x0[u] + kx * p.dil - p.pad, cy = y0[u] + ky * p.dil - p.pad;
+                        tma_load_4d(sa + (uint32_t)u * 2u * A_TILE_BYTES, &tmA_hi, fb, cc * TC_BK, cx, cy, img[u]);
+                        tma_load_4d(sa + (uint32_t)u * 2u * A_TILE_BYTES + A_TILE_BYTES, &tmA_lo, fb, cc * TC_BK, cx, cy, img[u]);
+                    }
+                    tma_load_2d(sa + a_bytes, &tmB_hi, fb, kb * TC_BK, n_idx * p.n_tile);
+                    tma_load_2d(sa + a_bytes + b_tile_bytes, &tmB_lo, fb, kb * TC_BK, n_idx * p.n_tile);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -215,18 +226,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
                     const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
-                    const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + A_TILE_BYTES);
-                    const uint64_t b_hi = make_smem_desc(sa + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_smem_desc(sa + 2 * A_TILE_BYTES + b_tile_bytes);
+                    const uint64_t b_hi = make_smem_desc(sa + a_bytes);
+                    const uint64_t b_lo = make_smem_desc(sa + a_bytes + b_tile_bytes);
                     // only the 16-channel steps that hold real channels (TMA zero-fills the rest)
                     const int cc = kb % p.cchunks;
                     const int ksteps = min(TC_BK / 16, (p.Cin - cc * TC_BK + 15) / 16);
-                    for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t koff = (uint64_t)(k * 32 >> 4);       // 16 fp16 = 32 bytes along K
-                        // small terms first, then the dominant hi*hi product
-                        umma_f16(d_tmem, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-                        umma_f16(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                        umma_f16(d_tmem, a_hi + koff, b_hi + koff, idesc, 1u);
+                    for (int u = 0; u < p.mt; ++u) {
+                        const uint64_t a_hi = make_smem_desc(sa + (uint32_t)u * 2u * A_TILE_BYTES);
+                        const uint64_t a_lo = make_smem_desc(sa + (uint32_t)u * 2u * A_TILE_BYTES + A_TILE_BYTES);
+                        const uint32_t d_u = d_tmem + (uint32_t)u * 128u;         // second pixel tile: columns +128 (mt=2 needs N <= 128)
+                        for (int k = 0; k < ksteps; ++k) {
+                            const uint64_t koff = (uint64_t)(k * 32 >> 4);       // 16 fp16 = 32 bytes along K
+                            // small terms first, then the dominant hi*hi product
+                            umma_f16(d_u, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                            umma_f16(d_u, a_hi + koff, b_lo + koff, idesc, 1u);
+                            umma_f16(d_u, a_hi + koff, b_hi + koff, idesc, 1u);
+                        }
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));                // frees the smem stage when the MMAs retire
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -247,14 +262,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t acc_phase = 0;
         const int tiles_x = p.W / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_idx = tile / p.n_tiles, n_idx = tile - m_idx * p.n_tiles;
+            const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
+            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+            tc_fence_after();
+          for (int u = 0; u < p.mt; ++u) {
+            const int m_idx = g_idx * p.mt + u;
+            if (m_idx >= p.m_tiles) break;
             const int img_l = m_idx / p.tiles_per_img, img = img_l + p.img0;
             const int t = m_idx - img_l * p.tiles_per_img;
             const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
             const long long pix = ((long long)img * p.H + y) * p.W + x;
-            mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + (uint32_t)u * 128u + ((uint32_t)(q * 32) << 16);
             const int co_tile = n_idx * p.n_tile;
             for (int c0 = half_id * 32; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 64) {
                 float v[32];
@@ -319,6 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                 }
             }
+          }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
@@ -384,7 +403,10 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;
     k.Cout = s.Cout; k.act = s.act; k.out_scale = s.out_scale;
     k.n_tile = s.n_tile; k.n_tiles = s.n_tiles;
-    const size_t stage_bytes = 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
+    // two pixel tiles per weight-tile load when both accumulators fit one TMEM stage (N <= 128) and two
+    // pipeline stages still fit in shared memory: halves the weight traffic from L2
+    k.mt = (s.n_tile <= 128 && s.mt_hint != 1) ? 2 : 1;
+    const size_t stage_bytes = (size_t)k.mt * 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
     int stages = (int)((227 * 1024 - 1024 - 1024) / stage_bytes);   // minus static smem slack and alignment pad
     k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
@@ -441,7 +463,7 @@ int tc_launch(const TcLayer& L, int batch, int img0, int num_sms, cudaStream_t s
     TcK k = L.k;
     k.m_tiles = batch * k.tiles_per_img;
     k.img0 = img0;
-    int total = k.m_tiles * k.n_tiles;
+    int total = ((k.m_tiles + k.mt - 1) / k.mt) * k.n_tiles;
     int grid = total < num_sms ? total : num_sms;
     const bool sp = k.out_fmt == DT_SPLIT16;
     switch (k.act) {

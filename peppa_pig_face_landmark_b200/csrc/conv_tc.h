@@ -9,6 +9,7 @@ namespace skps {
 struct TcK {                     // kernel parameters
     int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
     int img0;                    // first sample of this launch (sub-batch execution)
+    int mt;                      // pixel tiles per weight-tile load (1 or 2)
     int taps, kw, dil, pad, cchunks;
     int Cout, Cin, act, stages;
     float out_scale;             // exact power of two undoing the weight pre-scale
@@ -29,6 +30,7 @@ struct TcSetup {
     int kh, kw, dil, pad;
     int Cout, act, n_tile, n_tiles;
     float out_scale;
+    int mt_hint;                 // 1 forces single-tile mode
     const void* w_hi; const void* w_lo;           // device, (n_tiles*n_tile, K_pad) fp16
     const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
