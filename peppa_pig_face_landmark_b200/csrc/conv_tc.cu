@@ -131,7 +131,8 @@ __device__ __forceinline__ float v_at(const float* v, int j) {
 template <int ACT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, const TcK p) {
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo, const TcK p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
@@ -170,6 +171,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
+    // epilogue staging for TMA stores: one 16 KB buffer (128 rows x 32 channels, hi+lo or float32) per warp group
+    const uint32_t stage_out = tile_base + (uint32_t)p.stages * stage_bytes;
     const int m_groups = (p.m_tiles + p.mt - 1) / p.mt;
     const int total_tiles = m_groups * p.n_tiles;          // work items: (group of mt pixel tiles) x N tile
     const int kblocks = p.taps * p.cchunks;
@@ -282,6 +285,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 const long long o_el = pix * p.out_ld + p.out_coff + co0;
                 // vector path: whole groups of 8 channels (every Cout in the network but the 294-wide heat map and
                 // the 1-channel sSE map is a multiple of 8), unit channel stride, 16-byte aligned destination
+                // a 32-wide box may only be stored when its columns are all ours: a full chunk, or the chunk that ends
+                // the tensor (TMA clips at Cout); a ragged chunk in the middle (n_tile % 32 != 0) takes the direct path
+                if (p.tma_store && (nvalid == 32 || co0 + nvalid == p.Cout)) {
+                    // ---- bias/act/residual on all 32 columns (columns past Cout are clipped by the TMA store)
+                    const long long r_el = pix * p.res_ld + p.res_coff + co0;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float* w = v + 8 * g;
+                        if (8 * g < nvalid) {                         // nvalid is a multiple of 8 on this path
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + 8 * g);
+                            const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+                            w[0] = act_t<ACT>(fmaf(w[0], p.out_scale, b0.x)); w[1] = act_t<ACT>(fmaf(w[1], p.out_scale, b0.y));
+                            w[2] = act_t<ACT>(fmaf(w[2], p.out_scale, b0.z)); w[3] = act_t<ACT>(fmaf(w[3], p.out_scale, b0.w));
+                            w[4] = act_t<ACT>(fmaf(w[4], p.out_scale, b1.x)); w[5] = act_t<ACT>(fmaf(w[5], p.out_scale, b1.y));
+                            w[6] = act_t<ACT>(fmaf(w[6], p.out_scale, b1.z)); w[7] = act_t<ACT>(fmaf(w[7], p.out_scale, b1.w));
+                            if (p.res) {
+                                const float4 r0 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g);
+                                const float4 r1 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g + 4);
+                                w[0] += r0.x; w[1] += r0.y; w[2] += r0.z; w[3] += r0.w;
+                                w[4] += r1.x; w[5] += r1.y; w[6] += r1.z; w[7] += r1.w;
+                            }
+                        }
+                    }
+                    // ---- the staging buffer of this warp group must have been drained by its previous store
+                    const uint32_t sbuf = stage_out + (uint32_t)half_id * 16384u;
+                    if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
+                    if (OUT_SPLIT) {
+                        // rows of 64 B per plane: [hi plane 8 KB][lo plane 8 KB]
+                        const uint32_t rh = sbuf + (uint32_t)row * 64u, rl = rh + 8192u;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            uint32_t hp[4], lp[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float a0 = v[8 * g + 2 * j], a1 = v[8 * g + 2 * j + 1];
+                                const __half2 h2 = __floats2half2_rn(a0, a1);
+                                const float2 hf = __half22float2(h2);
+                                const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                                hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                                lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                            }
+                            // 64-byte swizzle (matches the tensor map): 16-byte chunk index ^= (row/2) % 4, so the
+                            // 32 rows a warp writes spread over all banks and TMA un-swizzles on the way out
+                            const uint32_t slot = (uint32_t)((g ^ (row >> 1)) & 3) * 16u;
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rh + slot), "r"(hp[0]), "r"(hp[1]), "r"(hp[2]), "r"(hp[3]) : "memory");
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rl + slot), "r"(lp[0]), "r"(lp[1]), "r"(lp[2]), "r"(lp[3]) : "memory");
+                        }
+                    } else {
+                        const uint32_t rf = sbuf + (uint32_t)row * 128u;
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) {
+                            const uint32_t slot = (uint32_t)((g ^ row) & 7) * 16u;      // 128-byte swizzle: chunk ^= row % 8
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rf + slot), "f"(v[4 * g]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3]) : "memory");
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
+                    if (q == 0 && lane == 0) {
+                        const int ty0 = (t / tiles_x) * p.bh, tx0 = (t % tiles_x) * p.bw;
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&tmO_hi), "r"(sbuf), "r"(co0), "r"(tx0), "r"(ty0), "r"(img) : "memory");
+                        if (OUT_SPLIT)
+                            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                         ::"l"(&tmO_lo), "r"(sbuf + 8192u), "r"(co0), "r"(tx0), "r"(ty0), "r"(img) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    continue;
+                }
                 const bool fast = (nvalid & 7) == 0 && p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 7) == 0;
                 if (fast) {
                     const int ng = nvalid >> 3;                       // warp-uniform
@@ -346,6 +418,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     }
 
+    if (p.tma_store && warp >= 4 && (warp & 3) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -407,10 +480,16 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     // pipeline stages still fit in shared memory: halves the weight traffic from L2
     k.mt = (s.n_tile <= 128 && s.mt_hint != 1) ? 2 : 1;
     const size_t stage_bytes = (size_t)k.mt * 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
-    int stages = (int)((227 * 1024 - 1024 - 1024) / stage_bytes);   // minus static smem slack and alignment pad
+    // TMA-store epilogue: full 128-byte lines instead of 16-byte pieces per thread.  Needs a unit-stride,
+    // 16-byte aligned destination whose channel count is a multiple of 8 (the swizzle-free box clips at Cout).
+    const int oes = s.out_fmt == DT_SPLIT16 ? 2 : 4;
+    k.tma_store = (s.out_cstride == 1 && (s.Cout % 8) == 0 && ((size_t)s.out_ld * oes) % 16 == 0 &&
+                   ((size_t)s.out_coff * oes) % 16 == 0 && s.tma_store_hint != 1) ? 1 : 0;
+    const size_t out_stage = k.tma_store ? 2 * 16384 : 0;
+    int stages = (int)((227 * 1024 - 1024 - 1024 - out_stage) / stage_bytes);   // minus static smem slack and alignment pad
     k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
-    L.smem_bytes = (int)(k.stages * stage_bytes + 1024);
+    L.smem_bytes = (int)(k.stages * stage_bytes + out_stage + 1024);
 
     // activations: (C, W, H, N) fp16, channel window [in_coff, in_coff+Cin) of rows of in_ld channels
     for (int plane = 0; plane < 2; ++plane) {
@@ -437,6 +516,27 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
+    if (k.tma_store) {
+        // output view (C, W, H, N); the staged tile is [row = pixel][32 channels] per plane, 64-byte (float16) or
+        // 128-byte (float32) rows written with the matching hardware swizzle (bank-conflict-free)
+        for (int plane = 0; plane < (s.out_fmt == DT_SPLIT16 ? 2 : 1); ++plane) {
+            cuuint64_t dims[4] = {(cuuint64_t)s.Cout, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
+            cuuint64_t strides[3] = {(cuuint64_t)s.out_ld * oes, (cuuint64_t)s.W * s.out_ld * oes,
+                                     (cuuint64_t)s.H * s.W * s.out_ld * oes};
+            cuuint32_t box[4] = {32, (cuuint32_t)k.bw, (cuuint32_t)k.bh, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            char* base = (char*)s.out + (size_t)s.out_coff * oes + (plane ? (size_t)s.out_plane * 2 : 0);
+            CUresult r = enc(plane ? &L.o_lo : &L.o_hi,
+                             s.out_fmt == DT_SPLIT16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                             base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             s.out_fmt == DT_SPLIT16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(out) failed: %d", (int)r);
+        }
+        if (s.out_fmt != DT_SPLIT16) L.o_lo = L.o_hi;
+    } else {
+        L.o_hi = L.a_hi; L.o_lo = L.a_hi;      // unused placeholders
+    }
     k.bias = s.bias ? s.bias : zero_bias();
     SKPS_CHECK(k.bias, "conv_tc: zero-bias allocation failed");
     k.Cin = s.Cin;
@@ -454,7 +554,7 @@ static int tc_launch_t(const TcLayer& L, const TcK& k, int grid, cudaStream_t st
                                        227 * 1024 - 1024));
         attr_set = true;
     }
-    conv_tc_kernel<ACT, SPLIT><<<grid, TC_THREADS, L.smem_bytes, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, k);
+    conv_tc_kernel<ACT, SPLIT><<<grid, TC_THREADS, L.smem_bytes, stream>>>(L.a_hi, L.a_lo, L.b_hi, L.b_lo, L.o_hi, L.o_lo, k);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -10,6 +10,7 @@ struct TcK {                     // kernel parameters
     int H, W, bw, bh, tiles_per_img, m_tiles, n_tiles, n_tile;
     int img0;                    // first sample of this launch (sub-batch execution)
     int mt;                      // pixel tiles per weight-tile load (1 or 2)
+    int tma_store;               // epilogue stages 32-channel chunks in smem and stores them with TMA
     int taps, kw, dil, pad, cchunks;
     int Cout, Cin, act, stages;
     float out_scale;             // exact power of two undoing the weight pre-scale
@@ -19,7 +20,7 @@ struct TcK {                     // kernel parameters
 };
 
 struct TcLayer {                 // prepared once per conv op at engine creation
-    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo, o_hi, o_lo;
     TcK k;
     int smem_bytes;
 };
@@ -31,6 +32,7 @@ struct TcSetup {
     int Cout, act, n_tile, n_tiles;
     float out_scale;
     int mt_hint;                 // 1 forces single-tile mode
+    int tma_store_hint;          // 1 disables the TMA-store epilogue
     const void* w_hi; const void* w_lo;           // device, (n_tiles*n_tile, K_pad) fp16
     const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;

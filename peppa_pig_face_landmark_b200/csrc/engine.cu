@@ -229,6 +229,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         }
         TcSetup s = {};
         { const char* env = getenv("SKPS_TC_MT"); s.mt_hint = (env && env[0] == '1') ? 1 : 0; }
+        { const char* env = getenv("SKPS_TC_TMA_STORE"); s.tma_store_hint = (env && env[0] == '0') ? 1 : 0; }
         s.H = in0.H; s.W = in0.W; s.Cin = in0.C; s.in_ld = in0.ld; s.in_coff = in0.c_off; s.max_batch = max_batch;
         s.in_base = in0.base; s.in_plane = in0.plane;
         s.kh = op.kh; s.kw = op.kw; s.dil = op.dh; s.pad = op.ph;
