@@ -280,12 +280,19 @@ def main():
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / reps
     peak_tf, peak_hbm, peak_src = measured_peaks()
+    bop = eng.plan.ops[best]
     k_flops = 2.0 * best_macs * B
     achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
     log("dominant kernel %.3f ms -> %.2f TFLOP/s" % (k_ms, achieved_tf))
     bop = eng.plan.ops[best]
+    # DRAM traffic of this launch from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    # dram__bytes_write.sum, profiles/r1_ncu_conv_tc_tail_v3.txt); only valid for the batch-256 conv2 launch
+    traffic = 0.538947e9 + 0.487993e9 if (B == 256 and bop.k[0] == 3 and bop.ins[0].C == 128 and bop.outs[0].C == 128) else None
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_algorithmic": 2 * B * bop.outs[0].H * bop.outs[0].W * 128 * 4,
+                "precision": "fp16 hi/lo split, 3 tcgen05 MMAs per K-step -> ceiling = peak/3",
+                "frac_of_split_ceiling": achieved_tf / (peak_tf / 3.0),
                 "kernel": "%s (%dx%d conv %d->%d @%dx%d, batch %d)" % (bop.name, bop.k[0], bop.k[1], bop.ins[0].C,
                                                                      bop.outs[0].C, bop.outs[0].H, bop.outs[0].W, B),
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms / args.steps),

@@ -49,7 +49,11 @@ class PlanInterp:
                 if op.ins[2] is not None:
                     x = x * rd(op.ins[2])
                 w = torch.from_numpy(getattr(op, 'w_ref', op.w)).permute(0, 3, 1, 2).contiguous()
-                y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b) if op.b is not None else None,
+                bias = torch.from_numpy(op.b) if op.b is not None else None
+                padc = op.outs[0].C - w.shape[0]          # zero-padded output channels (odd-width heat map)
+                if padc > 0:
+                    w = torch.cat([w, torch.zeros((padc,) + tuple(w.shape[1:]))])
+                y = F.conv2d(x.permute(0, 3, 1, 2), w, bias,
                              stride=op.s, padding=tuple(op.p), dilation=op.d)
                 y = _act(y, op.act).permute(0, 2, 3, 1)
                 if op.ins[1] is not None:

@@ -428,8 +428,19 @@ class _Lowerer:
                         pl.ops.append(P.Op(P.OP_SCALE_CH, [xin, gate], [sv], name=n.name + ":se_scale"))
                         xin, gate = sv, None
                     xin.buf.dtype = P.DT_SPLIT16
-                    n_tile, n_tiles = P.tc_tiling(w.shape[0])
-                    hi, lo, out_scale = P.pack_tc_weights(wk, n_tile, n_tiles)
+                    wk_tc, b_tc = wk, b
+                    if (out_v.C % 8 and out_v.c_off == 0 and out_v.c_stride == 1 and out_v.buf.C % 8 == 0
+                            and out_v.buf.C - out_v.C < 8):
+                        # odd channel count (the 294-wide heat map): also write the buffer's zero padding channels so
+                        # the epilogue can use whole 16-byte groups / TMA stores; consumers keep the logical view
+                        padc = out_v.buf.C - out_v.C
+                        wk_tc = np.concatenate([wk, np.zeros((padc,) + wk.shape[1:], np.float32)])
+                        b_tc = np.concatenate([b if b is not None else np.zeros(out_v.C, np.float32),
+                                               np.zeros(padc, np.float32)])
+                        out_v = P.View(out_v.buf, 0, 1, out_v.buf.C)
+                    n_tile, n_tiles = P.tc_tiling(wk_tc.shape[0])
+                    hi, lo, out_scale = P.pack_tc_weights(wk_tc, n_tile, n_tiles)
+                    b = b_tc
                     o = P.Op(P.OP_CONV, [xin, res, None], [out_v], f["act"], k, s, p[:2], d, hi, b,
                              flags | P.FLAG_TC, ints=[n_tile, n_tiles, 0, 0], floats=[out_scale], name=n.name)
                     o.w2 = lo
