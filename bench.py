@@ -211,13 +211,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks/throttle reasons are sampled from before the warm-up to the end of the timed region (nvidia-smi needs
+    # a few hundred ms to start, the timed region itself can be shorter than that)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.samples and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.05)
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_device(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record()
