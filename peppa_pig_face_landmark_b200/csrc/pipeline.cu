@@ -111,9 +111,15 @@ static int stage_frame(skps_pipeline* p, const uint8_t* frame, int H, int W, int
     if (on_device) {
         SKPS_CUDA(cudaMemcpyAsync(p->d_frame[p->cur], frame, bytes, cudaMemcpyDeviceToDevice, s));
     } else {
-        // pageable -> pinned staging keeps the H2D copy asynchronous and at full PCIe rate
-        memcpy(p->h_frame, frame, bytes);
-        SKPS_CUDA(cudaMemcpyAsync(p->d_frame[p->cur], p->h_frame, bytes, cudaMemcpyHostToDevice, s));
+        // frames already in pinned (page-locked) memory go straight to the GPU; pageable frames are first copied
+        // into the pipeline's pinned staging buffer so the H2D copy stays asynchronous and at full PCIe rate
+        cudaPointerAttributes attr;
+        bool pinned = cudaPointerGetAttributes(&attr, frame) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError();          // clear the "invalid value" a pageable pointer may leave behind
+            memcpy(p->h_frame, frame, bytes);
+        }
+        SKPS_CUDA(cudaMemcpyAsync(p->d_frame[p->cur], pinned ? frame : p->h_frame, bytes, cudaMemcpyHostToDevice, s));
     }
     *dptr = p->d_frame[p->cur];
     return 0;
