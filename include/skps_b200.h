@@ -76,6 +76,13 @@ SKPS_API int skps_engine_forward_host_f32(skps_engine* e, const float* input_nch
 SKPS_API int skps_engine_forward_host_u8(skps_engine* e, const uint8_t* input_nhwc, int batch,
                                 float* const* outputs, void* stream);
 
+/* Streaming host round trip (additive): two slots; while one batch computes the next one's pixels cross PCIe on a
+ * second stream.  `input` / `outputs[i]` [host, pinned] must stay valid until skps_engine_wait(slot) returns.
+ * Order of use: submit(0) submit(1) wait(0) submit(0) wait(1) ... */
+SKPS_API int skps_engine_submit_host_u8(skps_engine* e, int slot, const uint8_t* input_nhwc, int batch,
+                                        float* const* outputs);
+SKPS_API int skps_engine_wait(skps_engine* e, int slot);
+
 /* Debug/parity: copy internal buffer `buf` (N,H,W,C float32 NHWC) of the last forward to host. */
 SKPS_API int skps_engine_num_buffers(const skps_engine* e);
 SKPS_API int skps_engine_buffer_dims(const skps_engine* e, int buf, int* h, int* w, int* c, int* dtype);

@@ -73,6 +73,35 @@ class ONNXEngine:
         rt.check(self.lib.skps_engine_forward_host_u8(self.handle, x.ctypes.data, n, arr, self.stream.cuda_stream))
         return self._shape(outs, n)
 
+    def stream_u8(self, batches):
+        """Streaming variant of run_u8 for throughput: iterate over uint8 (N,H,W,3) host batches (pinned memory for
+        full overlap) and yield their outputs in order.  Two batches are in flight: while one computes, the next
+        one's pixels are copied to the GPU on a second stream; results land in pinned host buffers."""
+        torch = rt.require_cuda()
+        pin = [[torch.empty((self.max_batch, e), dtype=torch.float32).pin_memory() for e in self.out_elems]
+               for _ in range(2)]
+        arrs = [(C.c_void_p * self.n_out)(*[t.data_ptr() for t in pin[s]]) for s in range(2)]
+        pending = []            # (slot, batch size, keep-alive input)
+
+        def finish():
+            slot, n, _keep = pending.pop(0)
+            rt.check(self.lib.skps_engine_wait(self.handle, slot))
+            return self._shape([t[:n].numpy().copy() for t in pin[slot]], n)
+
+        i = 0
+        for x in batches:
+            x = np.ascontiguousarray(x, dtype=np.uint8)
+            if x.ndim != 4 or x.shape[3] != 3 or tuple(x.shape[1:3]) != self.in_hw:
+                raise ValueError("ONNXEngine.stream_u8: got %s, expected (N,%d,%d,3)" % (x.shape, *self.in_hw))
+            if len(pending) == 2:
+                yield finish()
+            slot = i & 1
+            rt.check(self.lib.skps_engine_submit_host_u8(self.handle, slot, x.ctypes.data, x.shape[0], arrs[slot]))
+            pending.append((slot, x.shape[0], x))
+            i += 1
+        while pending:
+            yield finish()
+
     def forward_device(self, x_u8, outputs=None, stream=None):
         """x_u8: torch uint8 CUDA tensor (N,H,W,3); outputs: optional list of float32 CUDA tensors.
         Asynchronous on `stream` (default: this engine's stream); returns the output tensors."""

@@ -51,6 +51,10 @@ struct skps_engine {
     std::vector<DwTmaLayer> dwt;          // per op; TMA-staged depthwise layers (valid flag)
     std::vector<UpcatTmaLayer> upt;       // per op; TMA-staged fused upsample+concat+depthwise
     bool use_dw_tma = true;
+    // streaming host round trip (skps_engine_submit_host_u8): 2 slots, H2D on its own stream
+    cudaStream_t s_copy = nullptr, s_compute = nullptr;
+    void* d_slot_in[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     struct Segment { int first, end, chunk; };
     std::vector<Segment> segments;        // ops [first,end) run `chunk` samples at a time (L2 residency)
 };
@@ -289,6 +293,14 @@ extern "C" SKPS_API void skps_engine_destroy(skps_engine* e) {
     cudaSetDevice(e->device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     for (void* p : e->dbuf) if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (e->d_slot_in[i]) cudaFree(e->d_slot_in[i]);
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_free[i]) cudaEventDestroy(e->ev_free[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    }
+    if (e->s_copy) cudaStreamDestroy(e->s_copy);
+    if (e->s_compute) cudaStreamDestroy(e->s_compute);
     if (e->d_weights) cudaFree(e->d_weights);
     if (e->d_stage_f32) cudaFree(e->d_stage_f32);
     if (e->d_in_f32) cudaFree(e->d_in_f32);
@@ -449,5 +461,52 @@ extern "C" SKPS_API int skps_engine_forward_host_f32(skps_engine* e, const float
     if (rc) return 1;
     if (copy_outputs(e, batch, outputs, cudaMemcpyDeviceToHost, s)) return 1;
     SKPS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Streaming host round trip: while batch i computes, batch i+1's pixels cross PCIe on a second stream.
+// Two slots; the caller alternates them:  submit(0) submit(1) wait(0) submit(0) wait(1) ...
+// `input` and `outputs[i]` should be pinned host memory and must stay valid until skps_engine_wait(slot).
+// ---------------------------------------------------------------------------------------------------
+static int ensure_streaming(skps_engine* e) {
+    if (e->s_copy) return 0;
+    const BufDesc& ib = e->bufs[e->input_buf];
+    SKPS_CUDA(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    SKPS_CUDA(cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        SKPS_CUDA(cudaMalloc(&e->d_slot_in[i], buf_bytes(ib) * (size_t)e->max_batch));
+        SKPS_CUDA(cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming));
+        SKPS_CUDA(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming));
+        SKPS_CUDA(cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+extern "C" SKPS_API int skps_engine_submit_host_u8(skps_engine* e, int slot, const uint8_t* input, int batch,
+                                                   float* const* outputs) {
+    SKPS_CHECK(e && input && (slot == 0 || slot == 1), "submit: bad arguments");
+    SKPS_CHECK(batch > 0 && batch <= e->max_batch, "submit: batch %d outside 1..%d", batch, e->max_batch);
+    SKPS_CUDA(cudaSetDevice(e->device));
+    if (ensure_streaming(e)) return 1;
+    const BufDesc& ib = e->bufs[e->input_buf];
+    const size_t in_bytes = buf_bytes(ib) * (size_t)batch;
+    // the slot's staging buffer is free once the compute that consumed it has copied it out (ev_free)
+    SKPS_CUDA(cudaStreamWaitEvent(e->s_copy, e->ev_free[slot], 0));
+    SKPS_CUDA(cudaMemcpyAsync(e->d_slot_in[slot], input, in_bytes, cudaMemcpyHostToDevice, e->s_copy));
+    SKPS_CUDA(cudaEventRecord(e->ev_in[slot], e->s_copy));
+    SKPS_CUDA(cudaStreamWaitEvent(e->s_compute, e->ev_in[slot], 0));
+    SKPS_CUDA(cudaMemcpyAsync(e->dbuf[e->input_buf], e->d_slot_in[slot], in_bytes, cudaMemcpyDeviceToDevice, e->s_compute));
+    SKPS_CUDA(cudaEventRecord(e->ev_free[slot], e->s_compute));
+    if (enqueue(e, batch, e->s_compute)) return 1;
+    if (copy_outputs(e, batch, outputs, cudaMemcpyDeviceToHost, e->s_compute)) return 1;
+    SKPS_CUDA(cudaEventRecord(e->ev_done[slot], e->s_compute));
+    return 0;
+}
+
+extern "C" SKPS_API int skps_engine_wait(skps_engine* e, int slot) {
+    SKPS_CHECK(e && (slot == 0 || slot == 1) && e->s_copy, "wait: nothing submitted");
+    SKPS_CUDA(cudaSetDevice(e->device));
+    SKPS_CUDA(cudaEventSynchronize(e->ev_done[slot]));
     return 0;
 }

@@ -39,6 +39,8 @@ SIGNATURES = {
     "skps_engine_forward": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "skps_engine_forward_host_f32": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "skps_engine_forward_host_u8": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp]),
+    "skps_engine_submit_host_u8": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, c_vp]),
+    "skps_engine_wait": (C.c_int, [c_vp, C.c_int]),
     "skps_engine_num_buffers": (C.c_int, [c_vp]),
     "skps_engine_buffer_dims": (C.c_int, [c_vp, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p]),
     "skps_engine_read_buffer": (C.c_int, [c_vp, C.c_int, C.c_int, c_vp]),

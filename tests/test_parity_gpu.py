@@ -182,6 +182,20 @@ def test_student_batch256_invariance():
     assert np.isfinite(lm).all() and np.isfinite(sc).all()
 
 
+def test_streaming_host_api_matches_blocking_call():
+    """ONNXEngine.stream_u8 (2 batches in flight, copy/compute overlap) returns exactly what run_u8 returns."""
+    import torch
+    from peppa_pig_face_landmark_b200 import ONNXEngine
+    eng = ONNXEngine(os.path.join(PRE, "kps_student.onnx"), max_batch=16)
+    batches = [torch.from_numpy(frames.noise_crops(n, seed=20 + i)).pin_memory().numpy()
+               for i, n in enumerate([16, 7, 16, 1, 12])]
+    ref = [eng.run_u8(b) for b in batches]
+    got = list(eng.stream_u8(iter(batches)))
+    assert len(got) == len(ref)
+    for (l0, s0), (l1, s1) in zip(ref, got):
+        assert np.array_equal(l0, l1) and np.array_equal(s0, s1)
+
+
 # ----------------------------------------------------------------------------- detector post
 def test_detector_kept_rows_match_golden(detector, golden):
     for name, fr in [("test1", frames.load_test1()), ("canvas640", frames.canvas_640()),
