@@ -276,3 +276,47 @@ def test_faceana_video_sequence_matches_reference_golden(golden):
     for t, fr in enumerate(video_frames()):
         res = facer.run(fr)
         _check_result(res, g, t, "video1080")
+
+
+# ----------------------------------------------------------------------------- edge cases vs the (pinned) oracle
+def _edge_frames():
+    """Odd frame sizes, faces hanging over the border (zero-padded crops), a frame of noise, a tiny frame."""
+    t1 = frames.load_test1()
+    out = {}
+    f = frames._background(719, 1279)
+    big = frames._resize(t1, 615, 409)
+    f[719 - 409:, 1279 - 615:] = big                    # face touching the bottom-right corner
+    f[5:5 + 273, 3:3 + 410] = t1                        # and one near the top-left corner
+    out["odd_719x1279_border_faces"] = f
+    g = np.full((333, 517, 3), 114, np.uint8)
+    g[30:30 + 273, 60:60 + 410] = t1
+    out["small_333x517"] = g
+    rng = np.random.default_rng(4)
+    out["noise_480x640"] = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
+    h = frames._background(1080, 1920)
+    h[200:200 + 273, -300:] = t1[:, :300]               # face cut by the right edge
+    out["hd_face_cut_by_edge"] = h
+    return out
+
+
+@pytest.mark.parametrize("name", ["odd_719x1279_border_faces", "small_333x517", "noise_480x640", "hd_face_cut_by_edge"])
+def test_faceana_edge_cases_match_oracle(name):
+    from Skps import FaceAna
+    from oracle.faceana_ref import FaceAnaRef
+    fr = _edge_frames()[name]
+    ref = FaceAnaRef().run(fr)
+    facer = FaceAna()
+    res = facer.run(fr)
+    assert len(res) == len(ref), (name, len(res), len(ref))
+    for a, b in zip(res, ref):
+        assert np.abs(a["kps"].astype(np.float64) - b["kps"]).max() <= KPS_TOL_PX, name
+        assert np.abs(a["scores"] - b["scores"]).max() <= SCORE_TOL, name
+        assert np.abs(np.asarray(a["box"], np.float64) - np.asarray(b["box"], np.float64)).max() <= KPS_TOL_PX, name
+    # second, unchanged frame: tracker path (no detector), still equal
+    ref2 = FaceAnaRef()
+    ref2.run(fr)
+    r2 = ref2.run(fr)
+    res2 = facer.run(fr)
+    assert len(res2) == len(r2)
+    for a, b in zip(res2, r2):
+        assert np.abs(a["kps"].astype(np.float64) - b["kps"]).max() <= KPS_TOL_PX, name
