@@ -263,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int row = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int store_i = 0;                 // TMA stores issued by this warp group so far
         const int tiles_x = p.W / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
@@ -309,8 +310,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         }
                     }
                     // ---- the staging buffer of this warp group must have been drained by its previous store
-                    const uint32_t sbuf = stage_out + (uint32_t)half_id * 16384u;
-                    if (q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    // staging buffers: one or two per warp group; with two, the store issued two chunks ago must have
+                    // drained (wait_group.read 1), so the store of the previous chunk overlaps this chunk's work
+                    const uint32_t sbuf = stage_out + (uint32_t)(half_id * p.out_bufs + (store_i % p.out_bufs)) * 16384u;
+                    if (q == 0 && lane == 0) {
+                        if (p.out_bufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    ++store_i;
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
                     if (OUT_SPLIT) {
                         // rows of 64 B per plane: [hi plane 8 KB][lo plane 8 KB]
@@ -485,8 +492,13 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     const int oes = s.out_fmt == DT_SPLIT16 ? 2 : 4;
     k.tma_store = (s.out_cstride == 1 && (s.Cout % 8) == 0 && ((size_t)s.out_ld * oes) % 16 == 0 &&
                    ((size_t)s.out_coff * oes) % 16 == 0 && s.tma_store_hint != 1) ? 1 : 0;
-    const size_t out_stage = k.tma_store ? 2 * 16384 : 0;
-    int stages = (int)((227 * 1024 - 1024 - 1024 - out_stage) / stage_bytes);   // minus static smem slack and alignment pad
+    // two staging buffers per epilogue warp group when the pipeline still gets its stages, else one
+    const size_t budget = 227 * 1024 - 1024 - 1024;                // minus static smem slack and alignment pad
+    const int want_stages = (int)((budget - 2 * 16384) / stage_bytes) > MAX_STAGES ? MAX_STAGES
+                                                                                  : (int)((budget - 2 * 16384) / stage_bytes);
+    k.out_bufs = (k.tma_store && (budget - 4 * 16384) / stage_bytes >= (size_t)want_stages) ? 2 : 1;
+    const size_t out_stage = k.tma_store ? (size_t)2 * k.out_bufs * 16384 : 0;
+    int stages = (int)((budget - out_stage) / stage_bytes);
     k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
     L.smem_bytes = (int)(k.stages * stage_bytes + out_stage + 1024);

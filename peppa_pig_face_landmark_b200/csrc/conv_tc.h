@@ -11,6 +11,7 @@ struct TcK {                     // kernel parameters
     int img0;                    // first sample of this launch (sub-batch execution)
     int mt;                      // pixel tiles per weight-tile load (1 or 2)
     int tma_store;               // epilogue stages 32-channel chunks in smem and stores them with TMA
+    int out_bufs;                // staging buffers per epilogue warp group (1 or 2)
     int taps, kw, dil, pad, cchunks;
     int Cout, Cin, act, stages;
     float out_scale;             // exact power of two undoing the weight pre-scale
