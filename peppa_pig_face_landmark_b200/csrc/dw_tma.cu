@@ -148,8 +148,13 @@ constexpr int LH = TH / 2 + 2, LW = TW / 2 + 2;      // low-res tile incl. halo
 
 __global__ void __launch_bounds__(DW_THREADS)
 upcat_tma_kernel(const __grid_constant__ CUtensorMap tm_low, const DwTmaK p, const int Hl, const int Wl) {
+    // Phase 0: TMA the low-res tile (6x10 pixels x 32 channels, float32).
+    // Phase 1: every up-sampled pixel of the (8+2)x(16+2) high-res window is interpolated exactly once into shared
+    //          memory (zero outside the high-res image = the depthwise conv's padding).
+    // Phase 2: ordinary register-tiled depthwise 3x3 out of shared memory (4 pixels x 4 channels per thread).
     constexpr int CB = 32, CG = CB / 4;
-    constexpr int BYTES = LH * LW * 128;
+    constexpr int LOW_BYTES = LH * LW * 128;
+    constexpr int UH = TH + 2, UW = TW + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x;
@@ -164,22 +169,14 @@ upcat_tma_kernel(const __grid_constant__ CUtensorMap tm_low, const DwTmaK p, con
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)BYTES) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)LOW_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
             ::"r"(sbase), "l"(&tm_low), "r"(bar_a), "r"(chunk * CB), "r"(lx0), "r"(ly0), "r"(n) : "memory");
     }
-    const int cg = tid % CG, pg = tid / CG;                  // 32 pixel groups = 4 x 8 blocks of 2x2
-    const int byl = pg / (TW / 2), bxl = pg % (TW / 2);
+    const int cg = tid % CG, pg = tid / CG;
     const int c = chunk * CB + cg * 4;
     const bool c_ok = c < p.C;
-    float4 w[9];
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c_ok) {
-        bias = *reinterpret_cast<const float4*>(p.bias + c);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k] = *reinterpret_cast<const float4*>(p.w + k * p.w_ld + c);
-    }
     __syncthreads();
     asm volatile(
         "{\n\t"
@@ -190,67 +187,64 @@ upcat_tma_kernel(const __grid_constant__ CUtensorMap tm_low, const DwTmaK p, con
         "bra UP_WAIT;\n\t"
         "UP_DONE:\n\t"
         "}\n" ::"r"(bar_a) : "memory");
+    const uint8_t* low = smem + (sbase - dsmem_u32(smem));
+    float* up = reinterpret_cast<float*>(const_cast<uint8_t*>(low) + LOW_BYTES);      // [UH][UW][32] float32
+    // ---- phase 1: bilinear x2 (half_pixel, align_corners=False): source = dst/2 - 0.25, edge-replicated
+    for (int item = pg; item < UH * UW; item += DW_THREADS / CG) {
+        const int uy = item / UW, ux = item - uy * UW;
+        const int ny = oy0 - 1 + uy, nx = ox0 - 1 + ux;                      // high-res coordinates
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ny >= 0 && ny < p.Ho && nx >= 0 && nx < p.Wo) {
+            const int y0 = (ny & 1) ? (ny >> 1) : (ny >> 1) - 1, x0 = (nx & 1) ? (nx >> 1) : (nx >> 1) - 1;
+            const float ly = (ny & 1) ? 0.25f : 0.75f, lx = (nx & 1) ? 0.25f : 0.75f;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const int ya = min(max(y0, 0), Hl - 1) - ly0, yb = min(max(y0 + 1, 0), Hl - 1) - ly0;
+            const int xa = min(max(x0, 0), Wl - 1) - lx0, xb = min(max(x0 + 1, 0), Wl - 1) - lx0;
+            const float4 p00 = *reinterpret_cast<const float4*>(low + (ya * LW + xa) * 128 + cg * 16);
+            const float4 p01 = *reinterpret_cast<const float4*>(low + (ya * LW + xb) * 128 + cg * 16);
+            const float4 p10 = *reinterpret_cast<const float4*>(low + (yb * LW + xa) * 128 + cg * 16);
+            const float4 p11 = *reinterpret_cast<const float4*>(low + (yb * LW + xb) * 128 + cg * 16);
+            v.x = hy * (hx * p00.x + lx * p01.x) + ly * (hx * p10.x + lx * p11.x);
+            v.y = hy * (hx * p00.y + lx * p01.y) + ly * (hx * p10.y + lx * p11.y);
+            v.z = hy * (hx * p00.z + lx * p01.z) + ly * (hx * p10.z + lx * p11.z);
+            v.w = hy * (hx * p00.w + lx * p01.w) + ly * (hx * p10.w + lx * p11.w);
+        }
+        *reinterpret_cast<float4*>(up + (item * CB + cg * 4)) = v;
+    }
+    __syncthreads();
     if (!c_ok) return;
-    const uint8_t* tile = smem + (sbase - dsmem_u32(smem));
-    const int oyb = oy0 + 2 * byl, oxb = ox0 + 2 * bxl;     // top-left output pixel of this thread's 2x2 block
-    if (oyb >= p.Ho || oxb >= p.Wo) return;
-    const int by = oyb >> 1, bx = oxb >> 1;                  // low-res pixel under the block
-    // columns/rows outside the high-res image are the depthwise conv's zero padding
-    const float vx0 = oxb > 0 ? 1.f : 0.f, vx3 = oxb + 2 < p.Wo ? 1.f : 0.f;
-    const float vy0 = oyb > 0 ? 1.f : 0.f, vy3 = oyb + 2 < p.Ho ? 1.f : 0.f;
-    float4 Hh[3][4];
-#define BLEND(dst, a, b, wa, wb, m)                                                   \
-    dst.x = (m) * ((wa) * a.x + (wb) * b.x); dst.y = (m) * ((wa) * a.y + (wb) * b.y); \
-    dst.z = (m) * ((wa) * a.z + (wb) * b.z); dst.w = (m) * ((wa) * a.w + (wb) * b.w);
+    // ---- phase 2: depthwise 3x3 from the staged window, PX = 4 outputs along x per thread
+    constexpr int PX = 4, SEGS = TW / PX;
+    const int row = pg / SEGS, xs = (pg % SEGS) * PX;
+    const float4 bias = *reinterpret_cast<const float4*>(p.bias + c);
+    float4 acc[PX] = {bias, bias, bias, bias};
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const int ly = min(max(by - 1 + r, 0), Hl - 1) - ly0;          // edge-replicated, in tile coordinates
-        float4 L[3];
+    for (int ky = 0; ky < 3; ++ky) {
+        float4 in[PX + 2];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const int lx = min(max(bx - 1 + q, 0), Wl - 1) - lx0;
-            L[q] = *reinterpret_cast<const float4*>(tile + (ly * LW + lx) * 128 + cg * 16);
-        }
-        BLEND(Hh[r][0], L[0], L[1], 0.75f, 0.25f, vx0)
-        BLEND(Hh[r][1], L[0], L[1], 0.25f, 0.75f, 1.f)
-        BLEND(Hh[r][2], L[1], L[2], 0.75f, 0.25f, 1.f)
-        BLEND(Hh[r][3], L[1], L[2], 0.25f, 0.75f, vx3)
-    }
-    float4 acc[2][2] = {{bias, bias}, {bias, bias}};
+        for (int j = 0; j < PX + 2; ++j)
+            in[j] = *reinterpret_cast<const float4*>(up + (((row + ky) * UW + xs + j) * CB + cg * 4));
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int a = r >> 1;
-        const float wa = (r & 1) ? 0.25f : 0.75f, wb = 1.f - wa;
-        const float m = r == 0 ? vy0 : (r == 3 ? vy3 : 1.f);
-        float4 U[4];
+        for (int kx = 0; kx < 3; ++kx) {
+            const float4 w = *reinterpret_cast<const float4*>(p.w + (ky * 3 + kx) * p.w_ld + c);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { BLEND(U[j], Hh[a][j], Hh[a + 1][j], wa, wb, m) }
-#pragma unroll
-        for (int oy = 0; oy < 2; ++oy) {
-            const int ky = r - oy;
-            if (ky < 0 || ky > 2) continue;
-#pragma unroll
-            for (int ox = 0; ox < 2; ++ox)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const float4 v = U[ox + kx], ww = w[ky * 3 + kx];
-                    acc[oy][ox].x = fmaf(v.x, ww.x, acc[oy][ox].x);
-                    acc[oy][ox].y = fmaf(v.y, ww.y, acc[oy][ox].y);
-                    acc[oy][ox].z = fmaf(v.z, ww.z, acc[oy][ox].z);
-                    acc[oy][ox].w = fmaf(v.w, ww.w, acc[oy][ox].w);
-                }
+            for (int q = 0; q < PX; ++q) {
+                const float4 v = in[q + kx];
+                acc[q].x = fmaf(v.x, w.x, acc[q].x); acc[q].y = fmaf(v.y, w.y, acc[q].y);
+                acc[q].z = fmaf(v.z, w.z, acc[q].z); acc[q].w = fmaf(v.w, w.w, acc[q].w);
+            }
         }
     }
-#undef BLEND
+    const int oy = oy0 + row;
+    if (oy >= p.Ho) return;
 #pragma unroll
-    for (int oy = 0; oy < 2; ++oy)
-#pragma unroll
-        for (int ox = 0; ox < 2; ++ox) {
-            float4 v = acc[oy][ox];
-            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-            st4(p.out, p.out_fmt, p.out_plane,
-                (((long long)n * p.Ho + oyb + oy) * p.Wo + oxb + ox) * p.out_ld + p.out_coff + c, v);
-        }
+    for (int q = 0; q < PX; ++q) {
+        const int ox = ox0 + xs + q;
+        if (ox >= p.Wo) break;
+        float4 a = acc[q];
+        a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act); a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+        st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -368,7 +362,7 @@ int upcat_tma_prepare(UpcatTmaLayer& L, const TView& low, const TView& skip, con
     k.out = out.base; k.out_fmt = out.fmt; k.out_plane = out.plane; k.out_ld = out.ld; k.out_coff = out.c_off;
     L.Hl = low.H; L.Wl = low.W;
     L.chunks = (low.C + 31) / 32;
-    L.smem_bytes = LH * LW * 128 + 128;
+    L.smem_bytes = LH * LW * 128 + (TH + 2) * (TW + 2) * 32 * 4 + 128;     // low tile + staged up-sampled window
     // skip channels: an ordinary depthwise layer over the channel slice [Cu, Ctot)
     TView o2 = out;
     o2.c_off += low.C; o2.C = skip.C;
