@@ -101,6 +101,14 @@ SKPS_API int skps_engine_run_op(skps_engine* e, int op_index, int batch, void* s
 SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi, const void* w_lo,
                                 const float* bias, int Cout, int ksize, int dil, int act, int n_tile, int n_tiles,
                                 float out_scale, const float* residual, int out_split, float* out);
+/* Same plus the conv stride (1 or 2: TMA element strides; out is N x H/stride x W/stride x Cout), the residual
+ * order (res_first != 0: act(conv + bias + residual), the ResNet/HRNet block of the Teacher, model.py:302-345)
+ * and the capacity max_batch >= N of the device buffers (maps smaller than 128 pixels share a tile between
+ * images; N not a multiple of that exercises the partial tile). */
+SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                                 const float* bias, int Cout, int ksize, int dil, int act, int n_tile, int n_tiles,
+                                 float out_scale, const float* residual, int out_split, float* out, int stride,
+                                 int res_first, int max_batch);
 
 /* ------------------------------------------------------------------ image kernels */
 

@@ -55,9 +55,13 @@ class PlanInterp:
                     w = torch.cat([w, torch.zeros((padc,) + tuple(w.shape[1:]))])
                 y = F.conv2d(x.permute(0, 3, 1, 2), w, bias,
                              stride=op.s, padding=tuple(op.p), dilation=op.d)
-                y = _act(y, op.act).permute(0, 2, 3, 1)
-                if op.ins[1] is not None:
-                    y = y + rd(op.ins[1])
+                y = y.permute(0, 2, 3, 1)
+                if op.ins[1] is not None and (op.flags & P.FLAG_RES_FIRST):
+                    y = _act(y + rd(op.ins[1]), op.act)          # conv-bn, += shortcut, relu
+                else:
+                    y = _act(y, op.act)
+                    if op.ins[1] is not None:
+                        y = y + rd(op.ins[1])
                 wr(op.outs[0], y)
             elif t == P.OP_DWCONV:
                 x = rd(op.ins[0])
@@ -97,6 +101,18 @@ class PlanInterp:
             elif t == P.OP_SCSE:
                 x = rd(op.ins[0])
                 wr(op.outs[0], x * rd(op.ins[1]) + x * rd(op.ins[2]))
+            elif t == P.OP_ADDN:
+                o = op.outs[0]
+                y = None
+                for v in op.ins:
+                    if v is None:
+                        continue
+                    x = rd(v)
+                    f = o.H // x.shape[1]
+                    if f > 1:
+                        x = x.repeat_interleave(f, 1).repeat_interleave(f, 2)
+                    y = x if y is None else y + x
+                wr(o, _act(y, op.act))
             elif t == P.OP_SCALE_CH:
                 wr(op.outs[0], rd(op.ins[0]) * rd(op.ins[1]))
             elif t == P.OP_DET_DECODE:

@@ -11,11 +11,11 @@ namespace skps {
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
-    OP_SCALE_CH = 12, OP_UPCAT_DW = 13
+    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
-enum { FLAG_IN_U8 = 1, FLAG_TC = 2 };
+enum { FLAG_IN_U8 = 1, FLAG_TC = 2, FLAG_RES_FIRST = 4 };
 enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
 
 struct View {            // 6 words
@@ -29,7 +29,8 @@ struct OpDesc {          // 64 words
     int32_t w_off, b_off, flags;
     int32_t i[4];
     float f[8];
-    int32_t pad[64 - (2 + 30 + 8 + 3 + 4 + 8)];
+    View in3;            // 4th input (OP_ADDN)
+    int32_t pad[64 - (2 + 30 + 8 + 3 + 4 + 8 + 6)];
 };
 static_assert(sizeof(OpDesc) == 64 * 4, "OpDesc must be 64 words");
 
@@ -188,6 +189,7 @@ struct ConvArgs {
     const float* w;               // [Cout][kh*kw][Cin]
     const float* bias;            // may be null
     int kh, kw, sh, sw, ph, pw, dh, dw, act, in_u8, batch;
+    int res_first;                // act(conv + bias + res) instead of act(conv + bias) + res
 };
 int launch_conv(const ConvArgs& a, cudaStream_t s);
 bool stem_conv_supported(const ConvArgs& a);
@@ -214,6 +216,8 @@ int launch_affine_act(const TView& in, const TView& out, const float* sc, const 
 int launch_scse(const TView& x, const TView& cse, const TView& sse, const TView& out, int batch, cudaStream_t s);
 int launch_det_decode(const TView* heads, const float* consts, const TView& out, int rows, int batch, cudaStream_t s);
 int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int batch, cudaStream_t s);
+// out = act(sum_j in_j), in_j read at (y >> shift_j, x >> shift_j): HRNet fuse layers (nearest upsample fused)
+int launch_addn(const TView* ins, int n_in, const TView& out, int act, int batch, cudaStream_t s);
 int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s);
 
 }  // namespace skps

@@ -20,6 +20,7 @@ struct ConvK {
     const float* gate; int gate_ld, gate_coff;     // per-sample (n, ci) input scale
     const float* w; const float* bias;
     int kh, kw, sh, sw, ph, pw, dh, dw, act;
+    int res_first;                                 // act(conv + bias + res) instead of act(conv + bias) + res
     int M;                                         // batch*Ho*Wo
 };
 
@@ -188,8 +189,8 @@ conv_igemm_kernel(const ConvK p) {
             if (co >= p.Cout) continue;
             float v = acc[i][j];
             if (p.bias) v += p.bias[co];
-            v = apply_act(v, p.act);
-            if (p.res) v += ld1(p.res, p.res_fmt, p.res_plane, rbase + co);
+            const float r = p.res ? ld1(p.res, p.res_fmt, p.res_plane, rbase + co) : 0.f;
+            v = p.res_first ? apply_act(v + r, p.act) : apply_act(v, p.act) + r;
             st1(p.out, p.out_fmt, p.out_plane, obase + (long long)co * p.out_cstride, v);
         }
     }
@@ -218,6 +219,7 @@ int launch_conv(const ConvArgs& a, cudaStream_t s) {
     k.w = a.w; k.bias = a.bias;
     k.kh = a.kh; k.kw = a.kw; k.sh = a.sh; k.sw = a.sw; k.ph = a.ph; k.pw = a.pw; k.dh = a.dh; k.dw = a.dw;
     k.act = a.act;
+    k.res_first = a.res.base ? a.res_first : 0;
     k.M = a.batch * k.Ho * k.Wo;
     SKPS_CHECK(a.in.c_stride == 1, "conv: strided input view");
     SKPS_CHECK(!a.res.base || a.res.c_stride == 1, "conv: strided residual view");

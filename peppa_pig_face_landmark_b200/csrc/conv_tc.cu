@@ -128,6 +128,32 @@ __device__ __forceinline__ float v_at(const float* v, int j) {
     return r;
 }
 
+// bias + (residual) + activation on 8 consecutive output channels of one pixel.
+// res_first = 0: act(acc*scale + bias) + res   (MobileNetV3 linear bottlenecks)
+// res_first = 1: act(acc*scale + bias + res)   (ResNet / HRNet blocks: conv-bn, add, relu)
+template <int ACT>
+__device__ __forceinline__ void epilogue8(float* w, const float4 b0, const float4 b1, const TcK& p, long long r_el) {
+    w[0] = fmaf(w[0], p.out_scale, b0.x); w[1] = fmaf(w[1], p.out_scale, b0.y);
+    w[2] = fmaf(w[2], p.out_scale, b0.z); w[3] = fmaf(w[3], p.out_scale, b0.w);
+    w[4] = fmaf(w[4], p.out_scale, b1.x); w[5] = fmaf(w[5], p.out_scale, b1.y);
+    w[6] = fmaf(w[6], p.out_scale, b1.z); w[7] = fmaf(w[7], p.out_scale, b1.w);
+    if (p.res) {
+        const float4 r0 = ld4(p.res, p.res_fmt, p.res_plane, r_el);
+        const float4 r1 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 4);
+        const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        if (p.res_first) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = act_t<ACT>(w[j] + r[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = act_t<ACT>(w[j]) + r[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = act_t<ACT>(w[j]);
+    }
+}
+
 template <int ACT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -188,11 +214,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 int img[2], y0[2], x0[2];
                 for (int u = 0; u < p.mt; ++u) {
                     const int m_idx = min(g_idx * p.mt + u, p.m_tiles - 1);     // odd tail: reload the last tile, result unused
-                    const int img_l = m_idx / p.tiles_per_img;
-                    const int t = m_idx - img_l * p.tiles_per_img;
+                    const int img_l = p.ipt > 1 ? m_idx * p.ipt : m_idx / p.tiles_per_img;
+                    const int t = p.ipt > 1 ? 0 : m_idx - img_l * p.tiles_per_img;
                     img[u] = img_l + p.img0;
-                    y0[u] = (t / tiles_x) * p.bh;
-                    x0[u] = (t % tiles_x) * p.bw;
+                    y0[u] = (t / tiles_x) * p.bh * p.stride;                    // input-space origin of the tile
+                    x0[u] = (t % tiles_x) * p.bw * p.stride;
                 }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -272,10 +298,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int u = 0; u < p.mt; ++u) {
             const int m_idx = g_idx * p.mt + u;
             if (m_idx >= p.m_tiles) break;
-            const int img_l = m_idx / p.tiles_per_img, img = img_l + p.img0;
-            const int t = m_idx - img_l * p.tiles_per_img;
+            const int img_l = p.ipt > 1 ? m_idx * p.ipt : m_idx / p.tiles_per_img, img = img_l + p.img0;
+            const int t = p.ipt > 1 ? 0 : m_idx - img_l * p.tiles_per_img;
+            // multi-image tiles (ipt > 1): bw = W, bh = ipt*H, so y runs past H into the next image and the linear
+            // pixel index below is still right; rows of images past the batch are computed but never stored
             const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
-            const long long pix = ((long long)img * p.H + y) * p.W + x;
+            const bool row_ok = p.ipt == 1 || img + y / p.H < p.img_end;
+            const long long pix = row_ok ? ((long long)img * p.H + y) * p.W + x : 0;
             const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + (uint32_t)u * 128u + ((uint32_t)(q * 32) << 16);
             const int co_tile = n_idx * p.n_tile;
             for (int c0 = half_id * 32; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 64) {
@@ -296,17 +325,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                         float* w = v + 8 * g;
                         if (8 * g < nvalid) {                         // nvalid is a multiple of 8 on this path
                             const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0 + 8 * g);
-                            const float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-                            w[0] = act_t<ACT>(fmaf(w[0], p.out_scale, b0.x)); w[1] = act_t<ACT>(fmaf(w[1], p.out_scale, b0.y));
-                            w[2] = act_t<ACT>(fmaf(w[2], p.out_scale, b0.z)); w[3] = act_t<ACT>(fmaf(w[3], p.out_scale, b0.w));
-                            w[4] = act_t<ACT>(fmaf(w[4], p.out_scale, b1.x)); w[5] = act_t<ACT>(fmaf(w[5], p.out_scale, b1.y));
-                            w[6] = act_t<ACT>(fmaf(w[6], p.out_scale, b1.z)); w[7] = act_t<ACT>(fmaf(w[7], p.out_scale, b1.w));
-                            if (p.res) {
-                                const float4 r0 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g);
-                                const float4 r1 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g + 4);
-                                w[0] += r0.x; w[1] += r0.y; w[2] += r0.z; w[3] += r0.w;
-                                w[4] += r1.x; w[5] += r1.y; w[6] += r1.z; w[7] += r1.w;
-                            }
+                            epilogue8<ACT>(w, __ldg(b4), __ldg(b4 + 1), p, r_el + 8 * g);
                         }
                     }
                     // ---- the staging buffer of this warp group must have been drained by its previous store
@@ -362,6 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     continue;
                 }
                 const bool fast = (nvalid & 7) == 0 && p.out_cstride == 1 && ((p.out_ld | (p.out_coff + co0)) & 7) == 0;
+                if (!row_ok) continue;
                 if (fast) {
                     const int ng = nvalid >> 3;                       // warp-uniform
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + co0);
@@ -370,17 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     for (int g = 0; g < 4; ++g) {
                         if (g < ng) {
                             float* w = v + 8 * g;
-                            const float4 b0 = __ldg(b4 + 2 * g), b1 = __ldg(b4 + 2 * g + 1);
-                            w[0] = act_t<ACT>(fmaf(w[0], p.out_scale, b0.x)); w[1] = act_t<ACT>(fmaf(w[1], p.out_scale, b0.y));
-                            w[2] = act_t<ACT>(fmaf(w[2], p.out_scale, b0.z)); w[3] = act_t<ACT>(fmaf(w[3], p.out_scale, b0.w));
-                            w[4] = act_t<ACT>(fmaf(w[4], p.out_scale, b1.x)); w[5] = act_t<ACT>(fmaf(w[5], p.out_scale, b1.y));
-                            w[6] = act_t<ACT>(fmaf(w[6], p.out_scale, b1.z)); w[7] = act_t<ACT>(fmaf(w[7], p.out_scale, b1.w));
-                            if (p.res) {
-                                const float4 r0 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g);
-                                const float4 r1 = ld4(p.res, p.res_fmt, p.res_plane, r_el + 8 * g + 4);
-                                w[0] += r0.x; w[1] += r0.y; w[2] += r0.z; w[3] += r0.w;
-                                w[4] += r1.x; w[5] += r1.y; w[6] += r1.z; w[7] += r1.w;
-                            }
+                            epilogue8<ACT>(w, __ldg(b4 + 2 * g), __ldg(b4 + 2 * g + 1), p, r_el + 8 * g);
                             if (OUT_SPLIT) {
                                 __half* oh = (__half*)p.out + o_el + 8 * g;
                                 uint4 hv, lv;
@@ -409,8 +419,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     const long long r_el = pix * p.res_ld + p.res_coff + co0;
 #pragma unroll 1
                     for (int j = 0; j < nvalid; ++j) {
-                        float f = act_t<ACT>(fmaf(v_at(v, j), p.out_scale, __ldg(p.bias + co0 + j)));
-                        if (p.res) f += ld1(p.res, p.res_fmt, p.res_plane, r_el + j);
+                        float f = fmaf(v_at(v, j), p.out_scale, __ldg(p.bias + co0 + j));
+                        const float r = p.res ? ld1(p.res, p.res_fmt, p.res_plane, r_el + j) : 0.f;
+                        f = p.res_first ? act_t<ACT>(f + r) : act_t<ACT>(f) + r;
                         st1(p.out, OUT_SPLIT ? DT_SPLIT16 : DT_F32, p.out_plane,
                             pix * p.out_ld + p.out_coff + (long long)(co0 + j) * p.out_cstride, f);
                     }
@@ -460,25 +471,32 @@ static const float* zero_bias() {
     return z;
 }
 
+// Ho x Wo = OUTPUT map: 128-pixel tiles must be whole row blocks of one image, or whole images (Ho*Wo | 128)
 bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff) {
     if (W < 8 || (Cin % 8) || (in_ld % 8) || (in_coff % 8)) return false;
     if (W >= TC_BM) return W % TC_BM == 0;
     if (TC_BM % W) return false;
+    if (H * W < TC_BM) return TC_BM % (H * W) == 0;
     return H % (TC_BM / W) == 0;
 }
 
 int tc_prepare(TcLayer& L, const TcSetup& s) {
     EncodeTiledFn enc = get_encode();
     SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
-    SKPS_CHECK(tc_shape_ok(s.H, s.W, s.Cin, s.in_ld, s.in_coff), "conv_tc: unsupported shape %dx%d Cin=%d ld=%d off=%d",
-               s.H, s.W, s.Cin, s.in_ld, s.in_coff);
+    const int stride = s.stride > 0 ? s.stride : 1;
+    SKPS_CHECK((stride == 1 || stride == 2) && s.H % stride == 0 && s.W % stride == 0, "conv_tc: stride %d on %dx%d", stride,
+               s.H, s.W);
+    const int Ho = s.H / stride, Wo = s.W / stride;
+    SKPS_CHECK(tc_shape_ok(Ho, Wo, s.Cin, s.in_ld, s.in_coff), "conv_tc: unsupported shape %dx%d Cin=%d ld=%d off=%d",
+               Ho, Wo, s.Cin, s.in_ld, s.in_coff);
     SKPS_CHECK(s.kh == s.kw && s.pad == s.dil * (s.kh - 1) / 2, "conv_tc: only 'same' square kernels");
     L.k = TcK();
     TcK& k = L.k;
-    k.H = s.H; k.W = s.W;
-    k.bw = s.W >= TC_BM ? TC_BM : s.W;
+    k.H = Ho; k.W = Wo; k.stride = stride;             // the kernel's H, W are the OUTPUT map
+    k.bw = Wo >= TC_BM ? TC_BM : Wo;
     k.bh = TC_BM / k.bw;
-    k.tiles_per_img = (s.H / k.bh) * (s.W / k.bw);
+    k.ipt = Ho * Wo < TC_BM ? TC_BM / (Ho * Wo) : 1;
+    k.tiles_per_img = k.ipt > 1 ? 1 : (Ho / k.bh) * (Wo / k.bw);
     k.taps = s.kh * s.kw; k.kw = s.kw; k.dil = s.dil; k.pad = s.pad;
     k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;
     k.Cout = s.Cout; k.act = s.act; k.out_scale = s.out_scale;
@@ -507,8 +525,11 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)s.in_ld * 2, (cuuint64_t)s.W * s.in_ld * 2, (cuuint64_t)s.H * s.W * s.in_ld * 2};
-        cuuint32_t box[4] = {TC_BK, (cuuint32_t)k.bw, (cuuint32_t)k.bh, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        // stride 2: TMA walks W and H with element stride 2; a box of 2*bw x 2*bh source elements lands as bw x bh in smem.
+        // small maps: the box spans `ipt` whole images (rows of the A tile = (n, y, x))
+        const cuuint32_t box_h = (cuuint32_t)(k.ipt > 1 ? Ho : k.bh);
+        cuuint32_t box[4] = {TC_BK, (cuuint32_t)(k.bw * stride), box_h * (cuuint32_t)stride, (cuuint32_t)k.ipt};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         void* base = (void*)((__half*)s.in_base + (plane ? s.in_plane : 0) + s.in_coff);
         CUresult r = enc(plane ? &L.a_lo : &L.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -532,10 +553,10 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
         // output view (C, W, H, N); the staged tile is [row = pixel][32 channels] per plane, 64-byte (float16) or
         // 128-byte (float32) rows written with the matching hardware swizzle (bank-conflict-free)
         for (int plane = 0; plane < (s.out_fmt == DT_SPLIT16 ? 2 : 1); ++plane) {
-            cuuint64_t dims[4] = {(cuuint64_t)s.Cout, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
-            cuuint64_t strides[3] = {(cuuint64_t)s.out_ld * oes, (cuuint64_t)s.W * s.out_ld * oes,
-                                     (cuuint64_t)s.H * s.W * s.out_ld * oes};
-            cuuint32_t box[4] = {32, (cuuint32_t)k.bw, (cuuint32_t)k.bh, 1};
+            cuuint64_t dims[4] = {(cuuint64_t)s.Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)s.max_batch};
+            cuuint64_t strides[3] = {(cuuint64_t)s.out_ld * oes, (cuuint64_t)Wo * s.out_ld * oes,
+                                     (cuuint64_t)Ho * Wo * s.out_ld * oes};
+            cuuint32_t box[4] = {32, (cuuint32_t)k.bw, (cuuint32_t)(k.ipt > 1 ? Ho : k.bh), (cuuint32_t)k.ipt};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             char* base = (char*)s.out + (size_t)s.out_coff * oes + (plane ? (size_t)s.out_plane * 2 : 0);
             CUresult r = enc(plane ? &L.o_lo : &L.o_hi,
@@ -555,6 +576,7 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.out = s.out; k.out_fmt = s.out_fmt; k.out_plane = s.out_plane; k.out_ld = s.out_ld; k.out_coff = s.out_coff;
     k.out_cstride = s.out_cstride;
     k.res = s.res; k.res_fmt = s.res_fmt; k.res_plane = s.res_plane; k.res_ld = s.res_ld; k.res_coff = s.res_coff;
+    k.res_first = s.res ? s.res_first : 0;
     return 0;
 }
 
@@ -573,8 +595,9 @@ static int tc_launch_t(const TcLayer& L, const TcK& k, int grid, cudaStream_t st
 
 int tc_launch(const TcLayer& L, int batch, int img0, int num_sms, cudaStream_t stream) {
     TcK k = L.k;
-    k.m_tiles = batch * k.tiles_per_img;
+    k.m_tiles = k.ipt > 1 ? (batch + k.ipt - 1) / k.ipt : batch * k.tiles_per_img;
     k.img0 = img0;
+    k.img_end = img0 + batch;
     int total = ((k.m_tiles + k.mt - 1) / k.mt) * k.n_tiles;
     int grid = total < num_sms ? total : num_sms;
     const bool sp = k.out_fmt == DT_SPLIT16;
@@ -608,22 +631,42 @@ using namespace skps;
 //   x      [host] float32 NHWC (N,H,W,Cin)
 //   w_hi/w_lo [host] float16 (rows, K_pad) as packed by plan.py:pack_tc_weights
 //   out    [host] float32 NHWC (N,H,W,Cout)
+extern "C" SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, const void* w_hi,
+                                            const void* w_lo, const float* bias, int Cout, int ksize, int dil, int act,
+                                            int n_tile, int n_tiles, float out_scale, const float* residual,
+                                            int out_split, float* out, int stride, int res_first, int max_batch);
+
 extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, int Cin, const void* w_hi,
                                            const void* w_lo, const float* bias, int Cout, int ksize, int dil, int act,
                                            int n_tile, int n_tiles, float out_scale, const float* residual,
                                            int out_split, float* out) {
+    return skps_debug_conv_tc2(x, N, H, W, Cin, w_hi, w_lo, bias, Cout, ksize, dil, act, n_tile, n_tiles, out_scale,
+                               residual, out_split, out, 1, 0, N);
+}
+
+// Same with a conv stride (1 or 2; out is N x H/stride x W/stride x Cout), the residual order
+// (res_first: act(conv + res) instead of act(conv) + res) and a buffer capacity max_batch >= N
+// (multi-image tiles write whole tiles: exercises the partial last tile).
+extern "C" SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, const void* w_hi,
+                                            const void* w_lo, const float* bias, int Cout, int ksize, int dil, int act,
+                                            int n_tile, int n_tiles, float out_scale, const float* residual,
+                                            int out_split, float* out, int stride, int res_first, int max_batch) {
     SKPS_CHECK(x && w_hi && w_lo && out, "debug_conv_tc: null argument");
-    const long long nin = (long long)N * H * W * Cin, nout = (long long)N * H * W * Cout;
+    SKPS_CHECK((stride == 1 || stride == 2) && max_batch >= N, "debug_conv_tc: bad stride/max_batch");
+    const int Ho = H / stride, Wo = W / stride;
+    const long long nin = (long long)N * H * W * Cin, nout = (long long)N * Ho * Wo * Cout;
+    const long long cin_cap = (long long)max_batch * H * W * Cin, cout_cap = (long long)max_batch * Ho * Wo * Cout;
     const int cchunks = (Cin + TC_BK - 1) / TC_BK;
     const size_t wbytes = (size_t)n_tiles * n_tile * ksize * ksize * cchunks * TC_BK * 2;
     float *d_x = nullptr, *d_bias = nullptr, *d_out = nullptr, *d_res = nullptr;
     __half *d_split = nullptr, *d_wh = nullptr, *d_wl = nullptr, *d_osplit = nullptr;
     SKPS_CUDA(cudaMalloc(&d_x, nin * 4));
-    SKPS_CUDA(cudaMalloc(&d_split, nin * 4));
+    SKPS_CUDA(cudaMalloc(&d_split, cin_cap * 4));
+    SKPS_CUDA(cudaMemset(d_split, 0, cin_cap * 4));
     SKPS_CUDA(cudaMalloc(&d_wh, wbytes));
     SKPS_CUDA(cudaMalloc(&d_wl, wbytes));
-    SKPS_CUDA(cudaMalloc(&d_out, nout * 4));
-    SKPS_CUDA(cudaMalloc(&d_osplit, nout * 4));
+    SKPS_CUDA(cudaMalloc(&d_out, cout_cap * 4));
+    SKPS_CUDA(cudaMalloc(&d_osplit, cout_cap * 4));
     SKPS_CUDA(cudaMemcpy(d_x, x, nin * 4, cudaMemcpyHostToDevice));
     SKPS_CUDA(cudaMemcpy(d_wh, w_hi, wbytes, cudaMemcpyHostToDevice));
     SKPS_CUDA(cudaMemcpy(d_wl, w_lo, wbytes, cudaMemcpyHostToDevice));
@@ -635,16 +678,16 @@ extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, 
         SKPS_CUDA(cudaMalloc(&d_res, nout * 4));
         SKPS_CUDA(cudaMemcpy(d_res, residual, nout * 4, cudaMemcpyHostToDevice));
     }
-    f32_to_split_kernel<<<(unsigned)((nin + 255) / 256), 256>>>(d_x, d_split, d_split + nin, nin);
+    f32_to_split_kernel<<<(unsigned)((nin + 255) / 256), 256>>>(d_x, d_split, d_split + cin_cap, nin);
     SKPS_CUDA(cudaGetLastError());
     TcSetup s = {};
-    s.H = H; s.W = W; s.Cin = Cin; s.in_ld = Cin; s.in_coff = 0; s.max_batch = N;
-    s.in_base = d_split; s.in_plane = nin;
-    s.kh = s.kw = ksize; s.dil = dil; s.pad = dil * (ksize - 1) / 2;
+    s.H = H; s.W = W; s.Cin = Cin; s.in_ld = Cin; s.in_coff = 0; s.max_batch = max_batch;
+    s.in_base = d_split; s.in_plane = cin_cap;
+    s.kh = s.kw = ksize; s.dil = dil; s.pad = dil * (ksize - 1) / 2; s.stride = stride; s.res_first = res_first;
     s.Cout = Cout; s.act = act; s.n_tile = n_tile; s.n_tiles = n_tiles; s.out_scale = out_scale;
     s.w_hi = d_wh; s.w_lo = d_wl; s.bias = d_bias;
     s.out = out_split ? (void*)d_osplit : (void*)d_out; s.out_fmt = out_split ? DT_SPLIT16 : DT_F32;
-    s.out_plane = nout; s.out_ld = Cout; s.out_coff = 0; s.out_cstride = 1;
+    s.out_plane = cout_cap; s.out_ld = Cout; s.out_coff = 0; s.out_cstride = 1;
     s.res = d_res; s.res_fmt = DT_F32; s.res_plane = 0; s.res_ld = Cout; s.res_coff = 0;
     TcLayer L;
     if (tc_prepare(L, s)) return 1;
@@ -656,7 +699,8 @@ extern "C" SKPS_API int skps_debug_conv_tc(const float* x, int N, int H, int W, 
     if (out_split) {
         // recombine hi+lo on the host side of the test
         __half* tmp = (__half*)malloc(nout * 4);
-        SKPS_CUDA(cudaMemcpy(tmp, d_osplit, nout * 4, cudaMemcpyDeviceToHost));
+        SKPS_CUDA(cudaMemcpy(tmp, d_osplit, nout * 2, cudaMemcpyDeviceToHost));
+        SKPS_CUDA(cudaMemcpy(tmp + nout, d_osplit + cout_cap, nout * 2, cudaMemcpyDeviceToHost));
         for (long long i = 0; i < nout; ++i) out[i] = __half2float(tmp[i]) + __half2float(tmp[nout + i]);
         free(tmp);
     } else {

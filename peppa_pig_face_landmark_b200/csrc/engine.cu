@@ -111,6 +111,7 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 a.kh = op.kh; a.kw = op.kw; a.sh = op.sh; a.sw = op.sw; a.ph = op.ph; a.pw = op.pw;
                 a.dh = op.dh; a.dw = op.dw; a.act = op.act; a.in_u8 = ((op.flags & FLAG_IN_U8) && !e->f32_mode) ? 1 : 0;
                 a.batch = batch;
+                a.res_first = (op.flags & FLAG_RES_FIRST) ? 1 : 0;
                 rc = launch_conv(a, s);
                 break;
             }
@@ -134,6 +135,13 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
             case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
+            case OP_ADDN: {
+                TView ins[4] = {in0, in1, in2, resolve(e, op.in3, b0)};
+                int n_in = 0;
+                while (n_in < 4 && ins[n_in].base) ++n_in;
+                rc = launch_addn(ins, n_in, out0, op.act, batch, s);
+                break;
+            }
             case OP_UPCAT_DW:
                 rc = e->upt[i].valid ? upcat_tma_launch(e->upt[i], batch, b0, s)
                                      : launch_upcat_dw(in0, in1, out0, w, b, op.act, batch, s);
@@ -227,7 +235,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         const OpDesc& op = e->ops[i];
         if (op.type != OP_CONV || !(op.flags & FLAG_TC)) continue;
         TView in0 = resolve(e, op.in[0]), res = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
-        if (in0.fmt != DT_SPLIT16 || in0.c_stride != 1 || op.in[2].buf >= 0 || op.sh != 1 || op.sw != 1) {
+        if (in0.fmt != DT_SPLIT16 || in0.c_stride != 1 || op.in[2].buf >= 0 || op.sh != op.sw) {
             set_error("op %d: tensor-core conv needs a SPLIT16 unit-stride input and no gate", i);
             return fail("tc");
         }
@@ -236,13 +244,14 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         { const char* env = getenv("SKPS_TC_TMA_STORE"); s.tma_store_hint = (env && env[0] == '0') ? 1 : 0; }
         s.H = in0.H; s.W = in0.W; s.Cin = in0.C; s.in_ld = in0.ld; s.in_coff = in0.c_off; s.max_batch = max_batch;
         s.in_base = in0.base; s.in_plane = in0.plane;
-        s.kh = op.kh; s.kw = op.kw; s.dil = op.dh; s.pad = op.ph;
+        s.kh = op.kh; s.kw = op.kw; s.dil = op.dh; s.pad = op.ph; s.stride = op.sh;
         s.Cout = out0.C; s.act = op.act; s.n_tile = op.i[0]; s.n_tiles = op.i[1]; s.out_scale = op.f[0];
         s.w_hi = e->d_weights + op.w_off; s.w_lo = e->d_weights + op.i[2];
         s.bias = op.b_off >= 0 ? e->d_weights + op.b_off : nullptr;
         s.out = out0.base; s.out_fmt = out0.fmt; s.out_plane = out0.plane; s.out_ld = out0.ld; s.out_coff = out0.c_off;
         s.out_cstride = out0.c_stride;
         s.res = res.base; s.res_fmt = res.fmt; s.res_plane = res.plane; s.res_ld = res.ld; s.res_coff = res.c_off;
+        s.res_first = (op.flags & FLAG_RES_FIRST) ? 1 : 0;
         if (op.dh != op.dw || op.ph != op.pw || tc_prepare(e->tc[i], s)) {
             char tmp[900];
             snprintf(tmp, sizeof(tmp), "%s", get_error());

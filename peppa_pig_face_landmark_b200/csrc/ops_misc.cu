@@ -502,8 +502,80 @@ int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int bat
 
 
 // ------------------------------------------------------------------------------------------
-// First layer of both networks: 3x3 stride-2 conv on uint8 pixels, 3 -> 16 channels (+ act).
-// One thread = one output pixel x 16 channels; weights and the v/255 table live in shared memory.
+// N-ary add with fused nearest up-sampling and activation: HRNet fuse layers
+// (timm hrnet.py HighResolutionModule.forward: y = sum_j fuse_layers[i][j](x[j]); relu) and any
+// residual Add the conv epilogues could not absorb.  Input j is read at (y >> sh_j, x >> sh_j), so
+// the nn.Upsample(scale_factor=2^k, mode='nearest') outputs are never written.
+// ------------------------------------------------------------------------------------------
+struct AddnK {
+    const void* in[4]; int ld[4], coff[4], cs[4], sh[4], fmt[4], H[4], W[4]; long long plane[4];
+    int n_in;
+    void* out; int out_ld, out_coff, out_cs, Ho, Wo, C, out_fmt; long long out_plane;
+    int act; long long total;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) addn_kernel(const AddnK p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
+    if (i >= (int)p.total) return;
+    const int CG = VEC ? (p.C >> 2) : p.C;
+    const int c = VEC ? (i % CG) * 4 : (i % CG);
+    const int pix = i / CG;
+    const int ox = pix % p.Wo;
+    const int t = pix / p.Wo;
+    const int oy = t % p.Ho;
+    const int n = t / p.Ho;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < p.n_in) {
+            const long long spix = ((long long)n * p.H[j] + (oy >> p.sh[j])) * p.W[j] + (ox >> p.sh[j]);
+            if (VEC) {
+                const float4 v = ld4(p.in[j], p.fmt[j], p.plane[j], spix * p.ld[j] + p.coff[j] + c);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            } else {
+                acc.x += ld1(p.in[j], p.fmt[j], p.plane[j], spix * p.ld[j] + p.coff[j] + (long long)c * p.cs[j]);
+            }
+        }
+    }
+    if (VEC) {
+        acc.x = apply_act(acc.x, p.act); acc.y = apply_act(acc.y, p.act);
+        acc.z = apply_act(acc.z, p.act); acc.w = apply_act(acc.w, p.act);
+        st4(p.out, p.out_fmt, p.out_plane, (long long)pix * p.out_ld + p.out_coff + c, acc);
+    } else {
+        st1(p.out, p.out_fmt, p.out_plane, (long long)pix * p.out_ld + p.out_coff + (long long)c * p.out_cs,
+            apply_act(acc.x, p.act));
+    }
+}
+
+int launch_addn(const TView* ins, int n_in, const TView& out, int act, int batch, cudaStream_t s) {
+    SKPS_CHECK(n_in >= 2 && n_in <= 4, "addn: %d inputs", n_in);
+    AddnK k = {};
+    bool vec = out.C % 4 == 0 && out.c_stride == 1 && ((out.ld | out.c_off) & 3) == 0;
+    for (int j = 0; j < n_in; ++j) {
+        const TView& v = ins[j];
+        int sh = 0;
+        while ((v.H << sh) < out.H) ++sh;
+        SKPS_CHECK(v.C == out.C && (v.H << sh) == out.H && (v.W << sh) == out.W, "addn: input %d shape %dx%dx%d vs %dx%dx%d",
+                   j, v.H, v.W, v.C, out.H, out.W, out.C);
+        k.in[j] = v.base; k.ld[j] = v.ld; k.coff[j] = v.c_off; k.cs[j] = v.c_stride; k.sh[j] = sh; k.fmt[j] = v.fmt;
+        k.H[j] = v.H; k.W[j] = v.W; k.plane[j] = v.plane;
+        vec = vec && v.c_stride == 1 && ((v.ld | v.c_off) & 3) == 0;
+    }
+    k.n_in = n_in;
+    k.out = out.base; k.out_ld = out.ld; k.out_coff = out.c_off; k.out_cs = out.c_stride; k.Ho = out.H; k.Wo = out.W;
+    k.C = out.C; k.out_fmt = out.fmt; k.out_plane = out.plane; k.act = act;
+    k.total = (long long)batch * out.H * out.W * (vec ? out.C / 4 : out.C);
+    SKPS_CHECK(k.total < (1ll << 31), "addn: tensor too large for 32-bit indexing");
+    if (vec) addn_kernel<true><<<blocks_for(k.total, 256), 256, 0, s>>>(k);
+    else addn_kernel<false><<<blocks_for(k.total, 256), 256, 0, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// First layer of the networks: 3x3 stride-2 conv on uint8 pixels, 3 -> 16 (student, detector) or 3 -> 64
+// (Teacher / HRNet stem) channels (+ act).  One thread = one output pixel x all output channels; weights and the v/255 table live in shared memory.
 // (kps_student.onnx node 1, yolov5n-0.5.onnx node 0; /255 as in face_landmark.py:46, face_detector.py:67)
 // ------------------------------------------------------------------------------------------
 struct StemK {
@@ -514,10 +586,11 @@ struct StemK {
     int act; long long total;
 };
 
+template <int CO>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
-    __shared__ __align__(16) float sw[27][16];
+    __shared__ __align__(16) float sw[27][CO];
     __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 27 * 16; i += blockDim.x) sw[i / 16][i % 16] = p.w[(i % 16) * 27 + i / 16];
+    for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) sw[i / CO][i % CO] = p.w[(i % CO) * 27 + i / CO];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.f);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
@@ -526,9 +599,9 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
     int t = i / p.Wo;
     int oy = t % p.Ho;
     int n = t / p.Ho;
-    float acc[16];
+    float acc[CO];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
     const uint8_t* img = p.in + (long long)n * p.H * p.W * 3;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -544,7 +617,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
                 const float x = lut[px[ci]];
                 const float4* wr = reinterpret_cast<const float4*>(sw[(ky * 3 + kx) * 3 + ci]);
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < CO / 4; ++g) {
                     const float4 w = wr[g];
                     acc[4 * g + 0] = fmaf(x, w.x, acc[4 * g + 0]);
                     acc[4 * g + 1] = fmaf(x, w.y, acc[4 * g + 1]);
@@ -556,7 +629,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
     }
     const long long o = (long long)i * p.out_ld + p.out_coff;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < CO / 4; ++g) {
         float4 v;
         v.x = apply_act(acc[4 * g + 0] + p.bias[4 * g + 0], p.act);
         v.y = apply_act(acc[4 * g + 1] + p.bias[4 * g + 1], p.act);
@@ -567,7 +640,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
 }
 
 bool stem_conv_supported(const ConvArgs& a) {
-    return a.in_u8 && a.in.C == 3 && a.in.ld == 3 && a.out.C == 16 && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2 &&
+    return a.in_u8 && a.in.C == 3 && a.in.ld == 3 && (a.out.C == 16 || a.out.C == 64) && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2 &&
            a.ph == 1 && a.pw == 1 && a.dh == 1 && a.dw == 1 && !a.res.base && !a.gate.base && a.bias &&
            a.out.c_stride == 1 && ((a.out.ld | a.out.c_off) & 3) == 0;
 }
@@ -579,7 +652,8 @@ int launch_stem_conv(const ConvArgs& a, cudaStream_t s) {
     k.Ho = a.out.H; k.Wo = a.out.W;
     k.w = a.w; k.bias = a.bias; k.act = a.act;
     k.total = (long long)a.batch * k.Ho * k.Wo;
-    stem_conv_kernel<<<blocks_for(k.total, 128), 128, 0, s>>>(k);
+    if (a.out.C == 16) stem_conv_kernel<16><<<blocks_for(k.total, 128), 128, 0, s>>>(k);
+    else stem_conv_kernel<64><<<blocks_for(k.total, 128), 128, 0, s>>>(k);     // Teacher (HRNet) stem: 3 -> 64
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

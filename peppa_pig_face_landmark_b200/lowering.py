@@ -6,6 +6,9 @@ Replaces what onnxruntime's graph optimiser + kernels do for the reference
 plan.py.  Patterns handled:
 
   Conv [+Sigmoid,Mul | +HardSigmoid,Mul | +Relu | +Sigmoid | +HardSigmoid] [+Add]   -> OP_CONV / OP_DWCONV
+  Conv + Add(residual) + Relu (ResNet / HRNet blocks of the Teacher, model.py:302-345) -> OP_CONV, FLAG_RES_FIRST
+  Add trees [+Relu] over branch tensors, nearest Resize x2^k folded in (HRNet fuse)    -> OP_ADDN
+  dense-conv tensors whose channel count is not a multiple of 8 (HRNet 18/36)          -> zero-padded channels
   ReduceMean(2,3) / GlobalAveragePool                                               -> OP_GAP
   Mul(x, gate[N,C,1,1]) feeding a Conv (squeeze-excite)                             -> conv input scale
   Mul(x,cSE) + Mul(x,sSE) -> Add (scSE attention)                                   -> OP_SCSE
@@ -65,6 +68,102 @@ def _fold(node, vals):
     raise LoweringError("cannot fold %s" % op)
 
 
+def pad_channels(g, mult=8):
+    """Zero-pad the channel count of tensors that live between dense convolutions up to a multiple of `mult`
+    (HRNet-w18's 18- and 36-channel branches -> 24 and 40) so that they meet the 16-byte alignment the TMA-fed
+    kernels need.  A tensor group = everything connected through Relu / Add / scale-Resize; it is padded only if
+    every producer is a dense Conv and every other consumer is a dense Conv: producers get zero output rows
+    (relu(0) = 0, 0 + 0 = 0 keeps the padding zero), consumers get zero input columns, so results are unchanged.
+    The original channel counts stay in attrs['_macs'] for the algorithmic MAC count."""
+    nodes, weights = g.nodes, dict(g.weights)
+    prod = {o: i for i, n in enumerate(nodes) for o in n.outputs}
+    uses = {}
+    for i, n in enumerate(nodes):
+        for x in n.inputs:
+            uses.setdefault(x, []).append(i)
+    parent = {}
+
+    def find(a):
+        parent.setdefault(a, a)
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    def data_inputs(n):
+        if n.op == "Relu":
+            return n.inputs[:1]
+        if n.op == "Add":
+            return n.inputs[:2]
+        if n.op == "Resize" and not (len(n.inputs) > 3 and n.inputs[3] != ""):
+            return n.inputs[:1]
+        return None
+
+    def dense(n):
+        return n.op == "Conv" and n.attrs.get("group", 1) == 1 and n.inputs[1] in weights
+
+    for n in nodes:
+        di = data_inputs(n)
+        if di:
+            for x in di:
+                parent[find(x)] = find(n.outputs[0])
+    roots = {}
+    for n in nodes:
+        if dense(n):
+            c = weights[n.inputs[1]].shape[0]
+            if c % mult and c > mult:
+                roots.setdefault(find(n.outputs[0]), c)
+    if not roots:
+        return g
+    members = {}
+    for name in list(parent) + [o for n in nodes for o in n.outputs]:
+        r = find(name)
+        if r in roots:
+            members.setdefault(r, set()).add(name)
+    todo = []
+    for r, names in members.items():
+        C, ok = roots[r], True
+        for t in names:
+            if t not in prod or t in g.outputs:
+                ok = False
+                break
+            pn = nodes[prod[t]]
+            if dense(pn):
+                ok &= weights[pn.inputs[1]].shape[0] == C
+            elif data_inputs(pn) is None:
+                ok = False
+            for ci in uses.get(t, []):
+                cn = nodes[ci]
+                di = data_inputs(cn)
+                if di is not None and t in di:
+                    continue
+                ok &= dense(cn) and cn.inputs[0] == t and t not in cn.inputs[1:]
+            if not ok:
+                break
+        if ok:
+            todo.append((names, C))
+    for names, C in todo:
+        Cp = -(-C // mult) * mult
+        for t in names:
+            pn = nodes[prod[t]]
+            if dense(pn) and weights[pn.inputs[1]].shape[0] == C:
+                w = weights[pn.inputs[1]]
+                pn.attrs.setdefault("_macs", [w.shape[0], w.shape[1]])
+                weights[pn.inputs[1]] = np.concatenate([w, np.zeros((Cp - C,) + w.shape[1:], w.dtype)])
+                if len(pn.inputs) > 2:
+                    b = weights[pn.inputs[2]]
+                    weights[pn.inputs[2]] = np.concatenate([b, np.zeros(Cp - C, b.dtype)])
+            for ci in uses.get(t, []):
+                cn = nodes[ci]
+                if dense(cn) and cn.inputs[0] == t:
+                    w = weights[cn.inputs[1]]
+                    if w.shape[1] == C:
+                        cn.attrs.setdefault("_macs", [w.shape[0], w.shape[1]])
+                        weights[cn.inputs[1]] = np.concatenate(
+                            [w, np.zeros((w.shape[0], Cp - C) + w.shape[2:], w.dtype)], axis=1)
+    return g._replace(weights=weights)
+
+
 class _T:
     """A logical NCHW tensor during lowering."""
     __slots__ = ("C", "H", "W", "home", "view", "scaled", "dtype")
@@ -83,6 +182,8 @@ _ACT_AFTER = {"Relu": P.ACT_RELU}
 class _Lowerer:
     def __init__(self, graph, name, in_hw, input_u8=True, use_tc=True):
         self.use_tc = use_tc
+        # stride-2 convs ride on TMA element strides (csrc/conv_tc.cu); SKPS_TC_STRIDE2=0 sends them back to the CUDA-core kernel
+        self.tc_strides = (1,) if os.environ.get("SKPS_TC_STRIDE2", "1") == "0" else (1, 2)
         self.g = graph
         self.plan = P.Plan(name)
         self.nodes = graph.nodes
@@ -92,6 +193,8 @@ class _Lowerer:
         for i, n in enumerate(self.nodes):
             for x in n.inputs:
                 self.uses.setdefault(x, []).append(i)
+        self.prod = {o: i for i, n in enumerate(self.nodes) for o in n.outputs}
+        self.add_inner = set()                # Add nodes folded into a later OP_ADDN
         self.absorbed = set()                 # node indices consumed by a fusion
         self.fused = {}                       # conv node idx -> dict(act, out, res)
         self.pending_copies = {}              # node idx -> [(src tensor, dst tensor)]
@@ -208,7 +311,10 @@ class _Lowerer:
             if a_.scaled and b_.scaled and a_.scaled[1] == b_.scaled[1] and {a_.scaled[0], b_.scaled[0]} == {"c", "s"}:
                 self._set(n.outputs[0], a_.C, a_.H, a_.W)
                 return
-            raise LoweringError("unfused Add %s" % n.name)
+            if a_.scaled or b_.scaled or a_.C != b_.C:
+                raise LoweringError("unfused Add %s" % n.name)
+            self._analyse_add(idx, n, a_, b_)
+            return
         if op == "Concat":
             assert n.attrs["axis"] == 1
             parts = [self.t[i] for i in ins]
@@ -251,6 +357,48 @@ class _Lowerer:
                 return
             raise LoweringError("unsupported Reshape %s -> %s" % (n.name, shape))
         raise LoweringError("unsupported op %s (%s)" % (op, n.name))
+
+    def _analyse_add(self, idx, n, a_, b_):
+        """Plain tensor Add: part of an OP_ADDN (sum tree, nearest Resize operands read in place, trailing Relu)."""
+        out = n.outputs[0]
+        H, W = max(a_.H, b_.H), max(a_.W, b_.W)
+        self._set(out, a_.C, H, W)
+        us = self.user_idx(out)
+        if len(us) == 1 and self.nodes[us[0]].op == "Add":
+            other = [i for i in self.nodes[us[0]].inputs if i != out]
+            if len(other) == 1 and other[0] in self.t and not self.t[other[0]].scaled:
+                self.add_inner.add(idx)          # folded into the Add that consumes it
+                return
+        leaves = []
+
+        def gather(name):
+            pi = self.prod.get(name)
+            if pi is not None and pi in self.add_inner:
+                for i in self.nodes[pi].inputs:
+                    gather(i)
+                return
+            pn = self.nodes[pi] if pi is not None else None
+            if (pn is not None and pn.op == "Resize" and pn.attrs.get("mode") == "nearest"
+                    and len(self.user_idx(name)) == 1 and pi not in self.absorbed):
+                src = self.t[pn.inputs[0]]
+                f = self.t[name].H // src.H
+                if src.H * f == self.t[name].H and src.W * f == self.t[name].W and f & (f - 1) == 0 \
+                        and src.home is None and not src.scaled:
+                    self.absorbed.add(pi)
+                    leaves.append(pn.inputs[0])
+                    return
+            leaves.append(name)
+
+        for i in n.inputs:
+            gather(i)
+        if len(leaves) > 4:
+            raise LoweringError("Add tree with %d operands at %s" % (len(leaves), n.name))
+        act, cur = P.ACT_NONE, out
+        if len(us) == 1 and self.nodes[us[0]].op == "Relu":
+            self.absorbed.add(us[0])
+            act, cur = P.ACT_RELU, self.nodes[us[0]].outputs[0]
+            self._set(cur, a_.C, H, W)
+        self.fused[idx] = dict(kind="addn", leaves=leaves, act=act, out=cur)
 
     def _is_alias(self, nm):
         return nm in getattr(self, "alias", set())
@@ -316,20 +464,26 @@ class _Lowerer:
             self._check_hsig(self.nodes[us[0]])
             act, cur = P.ACT_HSIGMOID, self.nodes[us[0]].outputs[0]
             self.absorbed.add(us[0])
-        res = None
+        res, res_first = None, False
         u2 = self.user_idx(cur)
         if len(u2) == 1 and self.nodes[u2[0]].op == "Add":
             add = self.nodes[u2[0]]
             other = [i for i in add.inputs if i != cur]
-            if len(other) == 1 and other[0] in self.t and not self.t[other[0]].scaled:
+            if len(other) == 1 and other[0] in self.t and not self.t[other[0]].scaled \
+                    and self.prod.get(other[0], -1) < idx:
                 o = self.t[other[0]]
                 if (o.C, o.H, o.W) == (t.C, t.H, t.W):
                     res = other[0]
                     self.absorbed.add(u2[0])
                     cur = add.outputs[0]
+                    u3 = self.user_idx(cur)
+                    if act == P.ACT_NONE and len(u3) == 1 and self.nodes[u3[0]].op == "Relu":
+                        # conv-bn, += shortcut, relu (timm BasicBlock / Bottleneck): the activation follows the add
+                        self.absorbed.add(u3[0])
+                        act, cur, res_first = P.ACT_RELU, self.nodes[u3[0]].outputs[0], True
         if cur != out:
             self._set(cur, t.C, t.H, t.W)
-        self.fused[idx] = dict(act=act, out=cur, res=res)
+        self.fused[idx] = dict(act=act, out=cur, res=res, res_first=res_first)
 
     @staticmethod
     def _check_hsig(node):
@@ -374,18 +528,24 @@ class _Lowerer:
             self._emit_det_decode()
 
     def _tc_eligible(self, xin, k, s, p, d, flags):
-        """Shapes csrc/conv_tc.cu handles: stride-1 'same' square convs whose 128-pixel tiles are whole
-        image-row blocks, channel windows aligned for TMA (16-byte rows of float16)."""
+        """Shapes csrc/conv_tc.cu handles: stride-1/2 'same' square convs whose 128-pixel output tiles are whole
+        image-row blocks (or whole images for maps under 128 pixels), channel windows aligned for TMA
+        (16-byte rows of float16)."""
         if not self.use_tc or (flags & P.FLAG_IN_U8) or xin.buf.dtype == P.DT_U8:
             return False
-        if list(s) != [1, 1] or k[0] != k[1] or d[0] != d[1] or p[0] != p[1] or p[0] != d[0] * (k[0] - 1) // 2:
+        if s[0] != s[1] or s[0] not in self.tc_strides or k[0] != k[1] or d[0] != d[1] or p[0] != p[1] \
+                or p[0] != d[0] * (k[0] - 1) // 2:
             return False
         if xin.c_stride != 1 or xin.C % 8 or xin.c_off % 8 or xin.buf.C % 8:
             return False
-        H, W = xin.H, xin.W
+        if xin.H % s[0] or xin.W % s[0]:
+            return False
+        H, W = xin.H // s[0], xin.W // s[0]              # output map: 128-pixel tiles = row blocks, or whole images
         if W >= 128:
             return W % 128 == 0
-        return W >= 8 and 128 % W == 0 and H % (128 // W) == 0
+        if W < 8 or 128 % W:
+            return False
+        return 128 % (H * W) == 0 if H * W < 128 else H % (128 // W) == 0
 
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
@@ -412,9 +572,10 @@ class _Lowerer:
             out_t = self.t[f["out"]]
             # heat-map head: fuse the decode tail instead of materialising the output tensor name
             out_v = self.view(f["out"])
-            flags = 0
+            flags = P.FLAG_RES_FIRST if f.get("res_first") else 0
             if ins[0] == self.input_name and self.input_u8:
                 flags |= P.FLAG_IN_U8
+            mc = a.get("_macs", [w.shape[0], w.shape[1]])          # channel counts before pad_channels()
             assert xin.c_stride == 1, "strided input view"
             if groups == 1:
                 wk = np.ascontiguousarray(w.transpose(0, 2, 3, 1))      # [Cout][kh][kw][Cin]
@@ -448,7 +609,7 @@ class _Lowerer:
                     o = P.Op(P.OP_CONV, [xin, res, gate], [out_v], f["act"], k, s, p[:2], d, wk, b, flags,
                              name=n.name)
                 o.w_ref = wk
-                pl.macs += out_t.C * out_t.H * out_t.W * w.shape[1] * k[0] * k[1]
+                pl.macs += mc[0] * out_t.H * out_t.W * mc[1] * k[0] * k[1]
             else:
                 assert groups == w.shape[0] and w.shape[1] == 1 and gate is None and not f.get("res")
                 wk = np.ascontiguousarray(w.reshape(w.shape[0], -1).T)    # [kh*kw][C]
@@ -492,6 +653,13 @@ class _Lowerer:
             return
         if op == "Mul":
             return      # lazily-applied SE / scSE scale
+        if op == "Add" and idx in self.add_inner:
+            return
+        if op == "Add" and self.fused.get(idx, {}).get("kind") == "addn":
+            f = self.fused[idx]
+            pl.ops.append(P.Op(P.OP_ADDN, [self.view(x) for x in f["leaves"]], [self.view(f["out"])], f["act"],
+                               name=n.name))
+            return
         if op == "Add":
             a_, b_ = self.t[ins[0]], self.t[ins[1]]
             c_t, s_t = (a_, b_) if a_.scaled[0] == "c" else (b_, a_)
@@ -616,7 +784,7 @@ def _fuse_upsample_concat_dw(pl):
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
-    g = load_onnx(onnx_path)
+    g = pad_channels(load_onnx(onnx_path))
     lw = _Lowerer(g, name or onnx_path, in_hw, input_u8, use_tc)
     lw.analyse()
     lw.emit()

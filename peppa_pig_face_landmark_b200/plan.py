@@ -28,6 +28,7 @@ OP_DET_DECODE = 10    # yolov5-face head decode -> (N,rows,16)
 OP_HM_DECODE = 11     # heat-map argmax + offset decode -> (N,196),(N,98)
 OP_SCALE_CH = 12      # x * gate[n,c]  (squeeze-excite applied ahead of a tensor-core conv)
 OP_UPCAT_DW = 13      # depthwise3x3(concat(bilinear_x2(low), skip)) without materialising the up-sampled tensor
+OP_ADDN = 14          # act(sum of up to 4 inputs), each optionally nearest-upsampled by 2^k (HRNet fuse layers)
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
 
@@ -94,6 +95,7 @@ class Op:
 
 FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
 FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo matrix (float16 bytes in the blob)
+FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
 
 
 class Plan:
@@ -162,6 +164,7 @@ class Plan:
             w += ints[:4]
             fl = np.asarray(list(op.floats) + [0.0] * (8 - len(op.floats)), np.float32)[:8]
             w += fl.view(np.int32).tolist()
+            w += op.ins[3].words() if len(op.ins) > 3 and op.ins[3] is not None else _NOVIEW     # 4th input (OP_ADDN)
             assert len(w) <= OP_WORDS, len(w)
             w += [0] * (OP_WORDS - len(w))
             ow += w

@@ -6,7 +6,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_split=False, seed=0):
+def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_split=False, seed=0, stride=1,
+         res_first=False, max_batch=None):
     import torch
     import torch.nn.functional as F
     from peppa_pig_face_landmark_b200 import plan as P, runtime as rt
@@ -15,27 +16,31 @@ def _run(N, H, W, Cin, Cout, k, dil, act, with_bias=True, with_res=False, out_sp
     x = rng.standard_normal((N, H, W, Cin)).astype(np.float32) * 2
     w = (rng.standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
     b = rng.standard_normal(Cout).astype(np.float32) if with_bias else None
-    res = rng.standard_normal((N, H, W, Cout)).astype(np.float32) if with_res else None
+    Ho, Wo = H // stride, W // stride
+    res = rng.standard_normal((N, Ho, Wo, Cout)).astype(np.float32) if with_res else None
     n_tile, n_tiles = P.tc_tiling(Cout)
     hi, lo, out_scale = P.pack_tc_weights(w, n_tile, n_tiles)
     hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
-    out = np.empty((N, H, W, Cout), np.float32)
-    rt.check(lib.skps_debug_conv_tc(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data,
-                                    b.ctypes.data if b is not None else None, Cout, k, dil, act, n_tile, n_tiles,
-                                    out_scale, res.ctypes.data if res is not None else None, 1 if out_split else 0,
-                                    out.ctypes.data))
+    out = np.empty((N, Ho, Wo, Cout), np.float32)
+    rt.check(lib.skps_debug_conv_tc2(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data,
+                                     b.ctypes.data if b is not None else None, Cout, k, dil, act, n_tile, n_tiles,
+                                     out_scale, res.ctypes.data if res is not None else None, 1 if out_split else 0,
+                                     out.ctypes.data, stride, 1 if res_first else 0, max_batch or N))
     xt = torch.from_numpy(x).permute(0, 3, 1, 2)
     wt = torch.from_numpy(w).permute(0, 3, 1, 2).contiguous()
-    y = F.conv2d(xt, wt, torch.from_numpy(b) if b is not None else None, padding=dil * (k - 1) // 2, dilation=dil)
+    y = F.conv2d(xt, wt, torch.from_numpy(b) if b is not None else None, stride=stride, padding=dil * (k - 1) // 2,
+                 dilation=dil)
+    if res is not None and res_first:
+        y = y + torch.from_numpy(res).permute(0, 3, 1, 2)
     if act == 1:
         y = torch.relu(y)
     elif act == 2:
         y = y * torch.clamp(y * np.float32(1 / 6) + 0.5, 0, 1)
     y = y.permute(0, 2, 3, 1).numpy()
-    if res is not None:
+    if res is not None and not res_first:
         y = y + res
     err = np.abs(out - y).max() / (np.abs(y).max() + 1e-9)
-    print('conv_tc', (N, H, W, Cin, Cout, k, dil, act), 'rel err %.3e' % err)
+    print('conv_tc', (N, H, W, Cin, Cout, k, dil, act, stride), 'rel err %.3e' % err)
     return err
 
 
@@ -63,3 +68,32 @@ def test_conv_tc_residual_and_split_output():
     assert _run(2, 32, 32, 120, 40, 1, 1, 0, with_res=True) < 1e-5
     assert _run(2, 64, 64, 128, 128, 3, 1, 1, out_split=True) < 1e-5
     assert _run(2, 16, 16, 672, 112, 1, 1, 0, with_bias=False, with_res=True, out_split=True) < 1e-5
+
+
+def test_conv_tc_residual_before_activation():
+    """conv-bn, += shortcut, relu of the Teacher's HRNet blocks (timm BasicBlock/Bottleneck; model.py:302-345)."""
+    assert _run(2, 64, 64, 24, 24, 3, 1, 1, with_res=True, res_first=True, out_split=True) < 1e-5
+    assert _run(2, 16, 16, 72, 72, 3, 1, 1, with_res=True, res_first=True) < 1e-5
+    assert _run(2, 64, 64, 64, 256, 1, 1, 1, with_res=True, res_first=True, out_split=True) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout, k, dil, act  -- stride 2 (TMA element strides), HRNet stem / transition / fuse convs
+    (2, 128, 128, 64, 64, 3, 1, 1),      # stem conv2: 64 -> 64, 128^2 -> 64^2
+    (2, 64, 64, 256, 40, 3, 1, 1),       # transition1 new branch (36 padded to 40)
+    (3, 64, 64, 24, 24, 3, 1, 1),        # fuse 18 -> 18 (padded to 24)
+    (2, 32, 32, 40, 72, 3, 1, 0),
+    (4, 16, 16, 72, 144, 3, 1, 0),       # output 8x8: two images per tile
+    (3, 16, 16, 72, 144, 3, 1, 1),       # ... with a partial last tile
+])
+def test_conv_tc_stride2(cfg):
+    err = _run(*cfg, stride=2)
+    assert err < 1e-5, (cfg, err)
+
+
+def test_conv_tc_small_maps_share_a_tile():
+    """8x8 maps (HRNet branch 4): one 128-row tile holds two images."""
+    assert _run(4, 8, 8, 144, 144, 3, 1, 1, with_res=True, res_first=True, out_split=True) < 1e-5
+    assert _run(5, 8, 8, 144, 144, 3, 1, 1) < 1e-5                      # odd batch: partial tile, TMA store clips
+    assert _run(3, 8, 8, 144, 72, 1, 1, 0, max_batch=8) < 1e-5         # spare capacity: the partial tile lands in unused slots
+    assert _run(3, 8, 8, 144, 24, 1, 1, 0, out_split=True, max_batch=4) < 1e-5
