@@ -193,6 +193,8 @@ struct ConvArgs {
 };
 int launch_conv(const ConvArgs& a, cudaStream_t s);
 bool stem_conv_supported(const ConvArgs& a);
+bool pw_small_supported(const ConvArgs& a);       // 1x1, Cout 16/24, Cin <= 96 on large maps (HBM-bound layers)
+int launch_pw_small(const ConvArgs& a, cudaStream_t s);
 int launch_stem_conv(const ConvArgs& a, cudaStream_t s);
 
 struct DwArgs {

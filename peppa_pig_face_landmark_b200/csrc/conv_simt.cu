@@ -209,6 +209,7 @@ static int launch_cfg(const ConvK& k, bool vec, bool in_u8, cudaStream_t s) {
 
 int launch_conv(const ConvArgs& a, cudaStream_t s) {
     if (stem_conv_supported(a)) return launch_stem_conv(a, s);
+    if (pw_small_supported(a)) return launch_pw_small(a, s);
     ConvK k;
     k.in = a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.H = a.in.H; k.W = a.in.W; k.Cin = a.in.C;
     k.in_fmt = a.in.fmt; k.in_plane = a.in.plane;

@@ -502,6 +502,107 @@ int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int bat
 
 
 // ------------------------------------------------------------------------------------------
+// Pointwise (1x1) convolution with few output channels (16 / 24) on CUDA cores: HBM-bound layers
+// (student blocks.0.0/conv_pw 16->16 @128^2, blocks.1.*/conv_pwl 64->24 and 72->24 @64^2) where a
+// 128 x N tensor-core tile is mostly padding and the per-tile pipeline overhead dominates.
+// One thread = PXT pixels x all COUT channels; inputs stream through registers 8 channels at a
+// time (one 16-byte load per float16 plane), the weights [ci][co] sit in shared memory and every
+// LDS.128 of 4 weights feeds 4*PXT FMAs.  fp32 accumulation in channel order (bias first).
+// ------------------------------------------------------------------------------------------
+struct PwK {
+    const void* in; int in_ld, in_coff, in_fmt; long long in_plane; int Cin;
+    void* out; int out_ld, out_coff, out_fmt; long long out_plane;
+    const void* res; int res_ld, res_coff, res_fmt; long long res_plane; int res_first;
+    const float* w; const float* bias;      // w: [Cout][Cin] (plan layout [Cout][1][1][Cin])
+    int act; int npix;
+};
+
+template <int COUT, int PXT>
+__global__ void __launch_bounds__(128) pw_small_kernel(const PwK p) {
+    extern __shared__ __align__(16) float pw_w[];          // [Cin][COUT]
+    for (int i = threadIdx.x; i < p.Cin * COUT; i += blockDim.x) {
+        const int ci = i / COUT, co = i - ci * COUT;
+        pw_w[i] = p.w[co * p.Cin + ci];
+    }
+    __syncthreads();
+    const int pix0 = blockIdx.x * (128 * PXT) + threadIdx.x;     // pixel q of this thread = pix0 + q*128
+    float acc[PXT][COUT];
+#pragma unroll
+    for (int q = 0; q < PXT; ++q)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[q][c] = p.bias ? __ldg(p.bias + c) : 0.f;
+    for (int ci = 0; ci < p.Cin; ci += 8) {
+        float8 x[PXT];
+#pragma unroll
+        for (int q = 0; q < PXT; ++q) {
+            const int pix = min(pix0 + q * 128, p.npix - 1);
+            x[q] = ld8(p.in, p.in_fmt, p.in_plane, (long long)pix * p.in_ld + p.in_coff + ci);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(pw_w + (ci + j) * COUT);
+#pragma unroll
+            for (int g = 0; g < COUT / 4; ++g) {
+                const float4 w = wr[g];
+#pragma unroll
+                for (int q = 0; q < PXT; ++q) {
+                    const float v = x[q].v[j];
+                    acc[q][4 * g + 0] = fmaf(v, w.x, acc[q][4 * g + 0]);
+                    acc[q][4 * g + 1] = fmaf(v, w.y, acc[q][4 * g + 1]);
+                    acc[q][4 * g + 2] = fmaf(v, w.z, acc[q][4 * g + 2]);
+                    acc[q][4 * g + 3] = fmaf(v, w.w, acc[q][4 * g + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PXT; ++q) {
+        const int pix = pix0 + q * 128;
+        if (pix >= p.npix) continue;
+#pragma unroll
+        for (int g = 0; g < COUT / 8; ++g) {
+            float8 o;
+            float8 r;
+            if (p.res) r = ld8(p.res, p.res_fmt, p.res_plane, (long long)pix * p.res_ld + p.res_coff + 8 * g);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a = acc[q][8 * g + j];
+                const float rr = p.res ? r.v[j] : 0.f;
+                o.v[j] = p.res_first ? apply_act(a + rr, p.act) : apply_act(a, p.act) + rr;
+            }
+            st8(p.out, p.out_fmt, p.out_plane, (long long)pix * p.out_ld + p.out_coff + 8 * g, o);
+        }
+    }
+}
+
+bool pw_small_supported(const ConvArgs& a) {
+    if (a.kh != 1 || a.kw != 1 || a.sh != 1 || a.sw != 1 || a.ph || a.pw || a.in_u8 || a.gate.base) return false;
+    if (a.out.C != 16 && a.out.C != 24) return false;
+    if (a.in.C % 8 || a.in.C > 96 || a.in.c_stride != 1 || a.out.c_stride != 1) return false;
+    if ((a.in.ld | a.in.c_off | a.out.ld | a.out.c_off) & 7) return false;
+    if (a.res.base && (a.res.c_stride != 1 || ((a.res.ld | a.res.c_off) & 7))) return false;
+    if ((long long)a.batch * a.out.H * a.out.W >= (1ll << 31) / 128) return false;
+    return a.out.H * a.out.W >= 1024;           // big maps only: small ones are latency-bound either way
+}
+
+int launch_pw_small(const ConvArgs& a, cudaStream_t s) {
+    PwK k;
+    k.in = a.in.base; k.in_ld = a.in.ld; k.in_coff = a.in.c_off; k.in_fmt = a.in.fmt; k.in_plane = a.in.plane; k.Cin = a.in.C;
+    k.out = a.out.base; k.out_ld = a.out.ld; k.out_coff = a.out.c_off; k.out_fmt = a.out.fmt; k.out_plane = a.out.plane;
+    k.res = a.res.base; k.res_ld = a.res.ld; k.res_coff = a.res.c_off; k.res_fmt = a.res.fmt; k.res_plane = a.res.plane;
+    k.res_first = a.res.base ? a.res_first : 0;
+    k.w = a.w; k.bias = a.bias; k.act = a.act;
+    k.npix = a.batch * a.out.H * a.out.W;
+    constexpr int PXT = 2;
+    const int blocks = (k.npix + 128 * PXT - 1) / (128 * PXT);
+    const size_t smem = (size_t)k.Cin * a.out.C * sizeof(float);
+    if (a.out.C == 16) pw_small_kernel<16, PXT><<<blocks, 128, smem, s>>>(k);
+    else pw_small_kernel<24, PXT><<<blocks, 128, smem, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // N-ary add with fused nearest up-sampling and activation: HRNet fuse layers
 // (timm hrnet.py HighResolutionModule.forward: y = sum_j fuse_layers[i][j](x[j]); relu) and any
 // residual Add the conv epilogues could not absorb.  Input j is read at (y >> sh_j, x >> sh_j), so

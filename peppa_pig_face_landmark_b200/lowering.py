@@ -183,6 +183,7 @@ class _Lowerer:
     def __init__(self, graph, name, in_hw, input_u8=True, use_tc=True):
         self.use_tc = use_tc
         # stride-2 convs ride on TMA element strides (csrc/conv_tc.cu); SKPS_TC_STRIDE2=0 sends them back to the CUDA-core kernel
+        self.pw_small = os.environ.get("SKPS_PW_SMALL", "1") != "0"
         self.tc_strides = (1,) if os.environ.get("SKPS_TC_STRIDE2", "1") == "0" else (1, 2)
         self.g = graph
         self.plan = P.Plan(name)
@@ -527,12 +528,15 @@ class _Lowerer:
         if self.det_heads:
             self._emit_det_decode()
 
-    def _tc_eligible(self, xin, k, s, p, d, flags):
+    def _tc_eligible(self, xin, k, s, p, d, flags, cout=0, gate=None):
         """Shapes csrc/conv_tc.cu handles: stride-1/2 'same' square convs whose 128-pixel output tiles are whole
         image-row blocks (or whole images for maps under 128 pixels), channel windows aligned for TMA
         (16-byte rows of float16)."""
         if not self.use_tc or (flags & P.FLAG_IN_U8) or xin.buf.dtype == P.DT_U8:
             return False
+        if self.pw_small and list(k) == [1, 1] and list(s) == [1, 1] and cout in (16, 24) and xin.C <= 96 \
+                and xin.H * xin.W >= 1024 and gate is None:
+            return False          # HBM-bound thin pointwise layer: csrc/ops_misc.cu pw_small_kernel (CUDA cores)
         if s[0] != s[1] or s[0] not in self.tc_strides or k[0] != k[1] or d[0] != d[1] or p[0] != p[1] \
                 or p[0] != d[0] * (k[0] - 1) // 2:
             return False
@@ -545,7 +549,9 @@ class _Lowerer:
             return W % 128 == 0
         if W < 8 or 128 % W:
             return False
-        return 128 % (H * W) == 0 if H * W < 128 else H % (128 // W) == 0
+        if H * W < 128:                                  # several whole images per tile (SKPS_TC_SMALL=0: CUDA-core kernel)
+            return 128 % (H * W) == 0 and os.environ.get("SKPS_TC_SMALL", "1") != "0"
+        return H % (128 // W) == 0
 
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
@@ -580,7 +586,7 @@ class _Lowerer:
             if groups == 1:
                 wk = np.ascontiguousarray(w.transpose(0, 2, 3, 1))      # [Cout][kh][kw][Cin]
                 res = self.view(f["res"]) if f.get("res") else None
-                if self._tc_eligible(xin, k, s, p, d, flags):
+                if self._tc_eligible(xin, k, s, p, d, flags, out_v.C, gate):
                     # tcgen05 path (csrc/conv_tc.cu): float16 hi/lo operands, input buffer in SPLIT16 format
                     if gate is not None:
                         # squeeze-excite scale cannot ride on a TMA-fed operand: apply it in its own pass

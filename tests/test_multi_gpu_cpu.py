@@ -38,3 +38,40 @@ def test_gloo_world2_sharding_and_timing(tmp_path):
     assert d["frames"] == [[0, 2, 4, 6, 8], [1, 3, 5, 7, 9]]
     assert d["t"] == 2.0                                         # max over ranks
     assert d["rate"] == 2 * 256 * 10 / 2.0
+
+
+WORKER2 = textwrap.dedent('''
+    import os, sys, json
+    import numpy as np
+    import torch, torch.distributed as dist
+    sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tools"))
+    from bench_pipeline import deal, pack_results
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    frames = deal(list(range(7)), rank, world)
+    # each rank "detects" rank+1 faces in its frame; rows are collected on every rank (config 5's optional gather)
+    res = [dict(box=np.full(4, 10 * rank + i, np.float32), kps=np.full((98, 2), i, np.float32),
+                scores=np.full(98, rank, np.float32)) for i in range(rank + 1)]
+    rows = torch.from_numpy(pack_results(res, 4))
+    allrows = [torch.zeros_like(rows) for _ in range(world)]
+    dist.all_gather(allrows, rows)
+    if rank == 0:
+        print(json.dumps({"frames": frames, "n": [int((r.abs().sum(1) > 0).sum()) for r in allrows],
+                          "box1": allrows[1][1, :4].tolist(), "shape": list(allrows[1].shape)}))
+    dist.destroy_process_group()
+''') % (ROOT, ROOT)
+
+
+def test_gloo_world2_pipeline_result_gather(tmp_path):
+    """tools/bench_pipeline.py's frame dealing and rank-0 collection of (box, landmarks, scores) rows."""
+    script = tmp_path / "w2.py"
+    script.write_text(WORKER2)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29612", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["frames"] == [0, 2, 4, 6] and d["shape"] == [4, 298]
+    assert d["n"] == [0, 2] or d["n"] == [1, 2]          # rank 0's single face has box 0 / kps 0 / score 0: all-zero row
+    assert d["box1"] == [11.0, 11.0, 11.0, 11.0]

@@ -1,4 +1,5 @@
-"""Summarise an ncu launch list (gpu__time_duration.sum, one student forward) per plan op."""
+"""Summarise an ncu launch list (gpu__time_duration.sum, one forward) per plan op:
+python tools/launch_table.py launches.csv [top] [student|teacher]"""
 import csv, sys, os
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
@@ -8,7 +9,11 @@ path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 lines = [l for l in open(path) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
-pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/kps_student.onnx'), (256, 256))
+if len(sys.argv) > 3 and sys.argv[3] == 'teacher':
+    from peppa_pig_face_landmark_b200 import teacher_graph
+    pl = lowering.lower(teacher_graph.ensure_teacher_onnx(), (256, 256))
+else:
+    pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/kps_student.onnx'), (256, 256))
 ops = []
 for op in pl.ops:
     ops.append(op)

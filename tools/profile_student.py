@@ -1,4 +1,4 @@
-"""One forward of the landmark network at batch 256 (for ncu captures)."""
+"""One forward of a landmark network (for ncu captures): python tools/profile_student.py [batch] [reps] [student|teacher]"""
 import os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -7,7 +7,13 @@ import frames
 from peppa_pig_face_landmark_b200 import ONNXEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-eng = ONNXEngine(os.path.join(ROOT, "peppa_pig_face_landmark_b200", "pretrained", "kps_student.onnx"), max_batch=B)
+model = sys.argv[3] if len(sys.argv) > 3 else "student"
+if model == "teacher":
+    from peppa_pig_face_landmark_b200 import teacher_graph
+    path = teacher_graph.ensure_teacher_onnx()
+else:
+    path = os.path.join(ROOT, "peppa_pig_face_landmark_b200", "pretrained", "kps_student.onnx")
+eng = ONNXEngine(path, max_batch=B)
 x = frames.noise_crops(B, seed=1)
 for _ in range(n):
     out = eng.run_u8(x)
