@@ -1,5 +1,5 @@
 """Teacher (HRNet-w18 + Decoder + heat-map head) inference graph, written as the .onnx file that
-`tools/convert_to_onnx.py --model teacher --img_size 256` would produce.
+`tools/convert_to_onnx.py --model teacher --img_size {128,256}` would produce.
 
 Reference: /root/reference/TRAIN/face_landmark/lib/core/base_trainer/model.py:302-345 (TeacherNet),
 :212-244 (Decoder), :64-98 (ASPP), :133-196 (DecoderBlock), :117-130 (SCSEModule), :511-554 (postp);
@@ -222,8 +222,8 @@ class _Builder:
 
 def build_teacher_onnx(path, size=256, seed=0, n_calib=4, student_onnx=STUDENT_ONNX):
     """Write the synthetic-weight Teacher graph to `path`; returns {'params', 'macs', 'nodes'}."""
-    if size != 256:
-        raise ValueError("the arg-max tail is taken from the 256-px student export: size must be 256")
+    if size % 32 or size < 64:
+        raise ValueError("teacher input size must be a multiple of 32 (README variants: 128, 256)")
     calib = torch.from_numpy(synthetic_crops(n_calib, size, seed + 1).transpose(0, 3, 1, 2).astype(np.float32) / 255.0)
     b = _Builder(seed, calib)
     E = "/teacher/encoder"
@@ -294,7 +294,12 @@ def build_teacher_onnx(path, size=256, seed=0, n_calib=4, student_onnx=STUDENT_O
         b.count_only(640, 7, 1, bias=True)              # self.fc (pose/cls head, unused at inference)
 
     # arg-max decode tail (model.py:511-554), traced nodes of the shipped student export, re-rooted on our heat map
+    if size != 256:
+        from .graph_tools import retarget_input_size
+        student_onnx = retarget_input_size(student_onnx, path + ".tail.tmp", size)    # postp constants for size/4 maps
     sg = load_onnx(student_onnx)
+    if size != 256:
+        os.remove(student_onnx)
     hm_idx = [i for i, n in enumerate(sg.nodes) if n.name == "/student/hm/Conv"][0]
     src = sg.nodes[hm_idx].outputs[0]
     tail = sg.nodes[hm_idx + 1:]

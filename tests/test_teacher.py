@@ -94,3 +94,45 @@ def test_teacher_cuda_fp32_fallback_path_agrees(teacher_onnx):
     a = ONNXEngine(teacher_onnx, max_batch=2).run_u8(crops)
     b = ONNXEngine(teacher_onnx, max_batch=2, use_tc=False).run_u8(crops)
     assert np.abs(a[0] - b[0]).max() * 256 < TOL_PX and np.abs(a[1] - b[1]).max() < TOL_SCORE
+
+
+def test_retargeted_128_exports_lower_and_match_oracle(tmp_path):
+    """README's @128 variants (8f-3): the shipped student export re-targeted to 128 px, and the Teacher built at
+    128 px, run through the same lowering; the plan interpreter must agree with the oracle executor."""
+    import frames
+    from peppa_pig_face_landmark_b200 import graph_tools, lowering, teacher_graph as T
+    from oracle.plan_interp import PlanInterp
+    from oracle.onnx_exec import Session
+    src = os.path.join(os.path.dirname(lowering.__file__), "pretrained", "kps_student.onnx")
+    s128 = graph_tools.retarget_input_size(src, str(tmp_path / "s128.onnx"), 128)
+    plan = lowering.lower(s128, (128, 128))
+    assert abs(plan.macs * 4 / 1482829696 - 1) < 0.01           # quarter of the @256 work (SE/FC layers do not scale)
+    crops = frames.crop_variants(2)[:, ::2, ::2].copy()
+    xy, sc = PlanInterp(plan).run(crops)
+    sess = Session(s128)
+    for i in range(2):
+        o, k = sess.run(crops[i].transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))
+        assert np.abs(xy[i] - o.reshape(-1)).max() * 128 < 1e-3 and np.abs(sc[i] - k.reshape(-1)).max() < 1e-4
+    t128 = str(tmp_path / "t128.onnx")
+    r = T.build_teacher_onnx(t128, size=128)
+    assert r["params"] == 12085570
+    plan = lowering.lower(t128, (128, 128))
+    crops = T.synthetic_crops(1, 128, 5)
+    xy, sc = PlanInterp(plan).run(crops)
+    rxy, rsc = _oracle64(t128, crops)
+    assert np.abs(xy - rxy).max() * 128 < TOL_PX and np.abs(sc - rsc).max() < TOL_SCORE
+
+
+@pytest.mark.gpu
+def test_student_128_cuda_matches_oracle(tmp_path):
+    import frames
+    from peppa_pig_face_landmark_b200 import ONNXEngine, graph_tools, lowering
+    from oracle.onnx_exec import Session
+    src = os.path.join(os.path.dirname(lowering.__file__), "pretrained", "kps_student.onnx")
+    s128 = graph_tools.retarget_input_size(src, str(tmp_path / "s128.onnx"), 128)
+    crops = frames.crop_variants(5)[:, ::2, ::2].copy()
+    xy, sc = ONNXEngine(s128, max_batch=5).run_u8(crops)          # odd batch: 8x8 maps share tiles between images
+    sess = Session(s128)
+    for i in range(5):
+        o, k = sess.run(crops[i].transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))
+        assert np.abs(xy[i] - o.reshape(-1)).max() * 128 < 1e-3 and np.abs(sc[i] - k.reshape(-1)).max() < 1e-4
