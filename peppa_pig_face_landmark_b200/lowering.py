@@ -534,7 +534,7 @@ class _Lowerer:
         (16-byte rows of float16)."""
         if not self.use_tc or (flags & P.FLAG_IN_U8) or xin.buf.dtype == P.DT_U8:
             return False
-        if self.pw_small and list(k) == [1, 1] and list(s) == [1, 1] and cout in (16, 24) and xin.C <= 96 \
+        if self.pw_small and list(k) == [1, 1] and list(s) == [1, 1] and cout == 16 and xin.C <= 32 \
                 and xin.H * xin.W >= 1024 and gate is None:
             return False          # HBM-bound thin pointwise layer: csrc/ops_misc.cu pw_small_kernel (CUDA cores)
         if s[0] != s[1] or s[0] not in self.tc_strides or k[0] != k[1] or d[0] != d[1] or p[0] != p[1] \

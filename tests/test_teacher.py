@@ -5,14 +5,19 @@ what is pinned is the architecture (parameter count = README's 11.53 "M" = 12 08
 thop figure) and, for the numbers, our CUDA path against the oracle's fp64 execution of the same generated
 .onnx file.  Tolerances are wider than the student's 1e-3 px because the synthetic random-weight network
 amplifies fp32 ordering noise: the oracle's own fp32 run differs from its fp64 run by ~1.5e-3 px / 4e-4 score
-(measured below), so the bar is 1e-2 px / 5e-3 score against fp64.
+(measured below), so the bar is 1e-2 px / 5e-3 score against fp64 for fp32 execution, and 6e-2 px / 2e-2 score for
+the tensor-core path (see TOL_PX_TC).
 """
 import os
 
 import numpy as np
 import pytest
 
-TOL_PX, TOL_SCORE = 1e-2, 5e-3
+TOL_PX, TOL_SCORE = 1e-2, 5e-3            # fp32 execution (plan interpreter, CUDA-core kernels) vs the fp64 oracle
+# tcgen05 path (fp16 hi/lo split, fp32 tensor-core accumulation): each conv is within 1e-5 relative of fp32
+# (tests/test_conv_tc_gpu.py, HRNet shapes included); through this random-weight network that per-layer noise is
+# amplified to 2.5e-2 px / 7e-3 score (measured on B200), against 9e-5 px for the trained student
+TOL_PX_TC, TOL_SCORE_TC = 6e-2, 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -49,8 +54,8 @@ def test_teacher_plan_matches_oracle_graph(teacher_onnx):
     tc = [o for o in convs if o.flags & P.FLAG_TC]
     # everything but the uint8 stem, the three 1x1-map FCs (ASPP pool, cSE) and the thin HBM-bound pointwise layers
     # (Cout 24 on >= 32x32 maps: pw_small_kernel) rides the tcgen05 kernel
-    thin = [o for o in convs if not (o.flags & P.FLAG_TC) and list(o.k) == [1, 1] and o.outs[0].C in (16, 24)
-            and o.outs[0].H * o.outs[0].W >= 1024]
+    thin = [o for o in convs if not (o.flags & P.FLAG_TC) and list(o.k) == [1, 1] and o.outs[0].C == 16
+            and o.ins[0].C <= 32 and o.outs[0].H * o.outs[0].W >= 1024]
     assert len(convs) - len(tc) - len(thin) == 4 and sum(o.type == P.OP_ADDN for o in plan.ops) == 40
     assert not any(o.type == P.OP_RESIZE_NEAREST and o.ins[0].H > 1 for o in plan.ops)   # HRNet upsamples are fused
     crops = T.synthetic_crops(2, 256, 99)
@@ -80,7 +85,7 @@ def test_teacher_cuda_matches_fp64_oracle(teacher_onnx):
     rxy, rsc = _oracle64(teacher_onnx, crops)
     dpx, dsc = np.abs(xy - rxy).max() * 256, np.abs(sc - rsc).max()
     print("teacher cuda vs fp64 oracle: %.2e px, %.2e score" % (dpx, dsc))
-    assert dpx < TOL_PX and dsc < TOL_SCORE
+    assert dpx < TOL_PX_TC and dsc < TOL_SCORE_TC
     # batch invariance: a sample alone equals the same sample inside the batch
     xy1, sc1 = eng.run_u8(crops[1:2])
     assert np.abs(xy1[0] - xy[1]).max() * 256 < 1e-4 and np.abs(sc1[0] - sc[1]).max() < 1e-5
@@ -93,7 +98,12 @@ def test_teacher_cuda_fp32_fallback_path_agrees(teacher_onnx):
     crops = T.synthetic_crops(2, 256, 11)
     a = ONNXEngine(teacher_onnx, max_batch=2).run_u8(crops)
     b = ONNXEngine(teacher_onnx, max_batch=2, use_tc=False).run_u8(crops)
-    assert np.abs(a[0] - b[0]).max() * 256 < TOL_PX and np.abs(a[1] - b[1]).max() < TOL_SCORE
+    rxy, rsc = _oracle64(teacher_onnx, crops)
+    d32 = (np.abs(b[0] - rxy).max() * 256, np.abs(b[1] - rsc).max())
+    dtc = (np.abs(a[0] - b[0]).max() * 256, np.abs(a[1] - b[1]).max())
+    print("teacher fp32 CUDA-core path vs fp64 oracle: %.2e px %.2e; tcgen05 path vs fp32 path: %.2e px %.2e" % (d32 + dtc))
+    assert d32[0] < TOL_PX and d32[1] < TOL_SCORE            # graph lowering + every non-tensor-core kernel, tight
+    assert dtc[0] < TOL_PX_TC and dtc[1] < TOL_SCORE_TC
 
 
 def test_retargeted_128_exports_lower_and_match_oracle(tmp_path):
