@@ -190,6 +190,8 @@ struct ConvArgs {
     const float* bias;            // may be null
     int kh, kw, sh, sw, ph, pw, dh, dw, act, in_u8, batch;
     int res_first;                // act(conv + bias + res) instead of act(conv + bias) + res
+    const float* w_host;          // host copies of w / bias (kernels that take weights as kernel parameters); may be null
+    const float* bias_host;
 };
 int launch_conv(const ConvArgs& a, cudaStream_t s);
 bool stem_conv_supported(const ConvArgs& a);

@@ -32,12 +32,13 @@ struct UpcatTmaLayer {
     CUtensorMap low;
     DwTmaK k;            // C = channels taken from `low`
     int Hl, Wl, chunks, smem_bytes;
+    const float* weff;   // [4][4][3][3][C] low-res stencil weights (plan.upcat_effective_weights); null = interpolate in smem
     DwTmaLayer skip;
     bool valid = false;
 };
 bool upcat_tma_supported(const TView& low, const TView& skip, const TView& out);
 int upcat_tma_prepare(UpcatTmaLayer& L, const TView& low, const TView& skip, const TView& out, const float* w,
-                      const float* bias, int act, int max_batch);
+                      const float* bias, const float* weff, int act, int max_batch);
 int upcat_tma_launch(const UpcatTmaLayer& L, int batch, int img0, cudaStream_t stream);
 
 }  // namespace skps

@@ -112,6 +112,8 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 a.dh = op.dh; a.dw = op.dw; a.act = op.act; a.in_u8 = ((op.flags & FLAG_IN_U8) && !e->f32_mode) ? 1 : 0;
                 a.batch = batch;
                 a.res_first = (op.flags & FLAG_RES_FIRST) ? 1 : 0;
+                a.w_host = op.w_off >= 0 ? e->h_weights.data() + op.w_off : nullptr;
+                a.bias_host = op.b_off >= 0 ? e->h_weights.data() + op.b_off : nullptr;
                 rc = launch_conv(a, s);
                 break;
             }
@@ -271,7 +273,9 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         if (op.type == OP_UPCAT_DW) {
             TView low = resolve(e, op.in[0]), skip = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
             if (!upcat_tma_supported(low, skip, out0)) continue;
-            if (upcat_tma_prepare(e->upt[i], low, skip, out0, e->d_weights + op.w_off, e->d_weights + op.b_off, op.act,
+            const char* eff = getenv("SKPS_UPCAT_EFF");
+            const float* weff = (op.i[0] > 0 && !(eff && eff[0] == '0')) ? e->d_weights + op.i[0] : nullptr;
+            if (upcat_tma_prepare(e->upt[i], low, skip, out0, e->d_weights + op.w_off, e->d_weights + op.b_off, weff, op.act,
                                   max_batch)) {
                 char tmp[900];
                 snprintf(tmp, sizeof(tmp), "%s", get_error());

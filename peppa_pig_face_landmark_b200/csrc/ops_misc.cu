@@ -684,16 +684,17 @@ int launch_addn(const TView* ins, int n_in, const TView& out, int act, int batch
 struct StemK {
     const uint8_t* in; int H, W;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, Ho, Wo;
-    const float* w;       // [16][3][3][3]  (co, ky, kx, ci)
-    const float* bias;
     int act; long long total;
 };
+// Weights travel in the kernel-parameter (constant) bank: with the tap loops fully unrolled every FMA takes its
+// weight as a constant operand, so the inner loop has no shared-memory weight traffic (the smem-broadcast version
+// was LDS-bound: 108 LDS.128 per 432 FMAs).  [tap*3+ci][co] layout.
+template <int CO>
+struct StemW { float w[27 * CO]; float b[CO]; };
 
 template <int CO>
-__global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
-    __shared__ __align__(16) float sw[27][CO];
+__global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p, const __grid_constant__ StemW<CO> W) {
     __shared__ float lut[256];
-    for (int i = threadIdx.x; i < 27 * CO; i += blockDim.x) sw[i / CO][i % CO] = p.w[(i % CO) * 27 + i / CO];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.f);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 32-bit on purpose: 64-bit div/mod is emulated
@@ -718,15 +719,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
 #pragma unroll
             for (int ci = 0; ci < 3; ++ci) {
                 const float x = lut[px[ci]];
-                const float4* wr = reinterpret_cast<const float4*>(sw[(ky * 3 + kx) * 3 + ci]);
 #pragma unroll
-                for (int g = 0; g < CO / 4; ++g) {
-                    const float4 w = wr[g];
-                    acc[4 * g + 0] = fmaf(x, w.x, acc[4 * g + 0]);
-                    acc[4 * g + 1] = fmaf(x, w.y, acc[4 * g + 1]);
-                    acc[4 * g + 2] = fmaf(x, w.z, acc[4 * g + 2]);
-                    acc[4 * g + 3] = fmaf(x, w.w, acc[4 * g + 3]);
-                }
+                for (int c = 0; c < CO; ++c) acc[c] = fmaf(x, W.w[((ky * 3 + kx) * 3 + ci) * CO + c], acc[c]);
             }
         }
     }
@@ -734,18 +728,31 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemK p) {
 #pragma unroll
     for (int g = 0; g < CO / 4; ++g) {
         float4 v;
-        v.x = apply_act(acc[4 * g + 0] + p.bias[4 * g + 0], p.act);
-        v.y = apply_act(acc[4 * g + 1] + p.bias[4 * g + 1], p.act);
-        v.z = apply_act(acc[4 * g + 2] + p.bias[4 * g + 2], p.act);
-        v.w = apply_act(acc[4 * g + 3] + p.bias[4 * g + 3], p.act);
+        v.x = apply_act(acc[4 * g + 0] + W.b[4 * g + 0], p.act);
+        v.y = apply_act(acc[4 * g + 1] + W.b[4 * g + 1], p.act);
+        v.z = apply_act(acc[4 * g + 2] + W.b[4 * g + 2], p.act);
+        v.w = apply_act(acc[4 * g + 3] + W.b[4 * g + 3], p.act);
         st4(p.out, p.out_fmt, p.out_plane, o + 4 * g, v);
     }
 }
 
 bool stem_conv_supported(const ConvArgs& a) {
     return a.in_u8 && a.in.C == 3 && a.in.ld == 3 && (a.out.C == 16 || a.out.C == 64) && a.kh == 3 && a.kw == 3 && a.sh == 2 && a.sw == 2 &&
-           a.ph == 1 && a.pw == 1 && a.dh == 1 && a.dw == 1 && !a.res.base && !a.gate.base && a.bias &&
+           a.ph == 1 && a.pw == 1 && a.dh == 1 && a.dw == 1 && !a.res.base && !a.gate.base && a.bias && a.w_host &&
+           a.bias_host &&
            a.out.c_stride == 1 && ((a.out.ld | a.out.c_off) & 3) == 0;
+}
+
+template <int CO>
+static int launch_stem_t(const StemK& k, const ConvArgs& a, cudaStream_t s) {
+    StemW<CO> W;                                  // host copy of [Cout][ky][kx][ci] -> [tap*3+ci][co]
+    for (int co = 0; co < CO; ++co) {
+        for (int j = 0; j < 27; ++j) W.w[j * CO + co] = a.w_host[co * 27 + j];
+        W.b[co] = a.bias_host[co];
+    }
+    stem_conv_kernel<CO><<<blocks_for(k.total, 128), 128, 0, s>>>(k, W);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_stem_conv(const ConvArgs& a, cudaStream_t s) {
@@ -753,12 +760,9 @@ int launch_stem_conv(const ConvArgs& a, cudaStream_t s) {
     k.in = (const uint8_t*)a.in.base; k.H = a.in.H; k.W = a.in.W;
     k.out = a.out.base; k.out_fmt = a.out.fmt; k.out_plane = a.out.plane; k.out_ld = a.out.ld; k.out_coff = a.out.c_off;
     k.Ho = a.out.H; k.Wo = a.out.W;
-    k.w = a.w; k.bias = a.bias; k.act = a.act;
+    k.act = a.act;
     k.total = (long long)a.batch * k.Ho * k.Wo;
-    if (a.out.C == 16) stem_conv_kernel<16><<<blocks_for(k.total, 128), 128, 0, s>>>(k);
-    else stem_conv_kernel<64><<<blocks_for(k.total, 128), 128, 0, s>>>(k);     // Teacher (HRNet) stem: 3 -> 64
-    SKPS_CUDA(cudaGetLastError());
-    return 0;
+    return a.out.C == 16 ? launch_stem_t<16>(k, a, s) : launch_stem_t<64>(k, a, s);     // 64: Teacher (HRNet) stem
 }
 
 // ------------------------------------------------------------------------------------------

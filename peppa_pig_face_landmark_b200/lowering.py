@@ -784,6 +784,7 @@ def _fuse_upsample_concat_dw(pl):
         d.type = P.OP_UPCAT_DW
         x.buf.name += ":skip-only"         # the first `cu` channels of this buffer are never written any more
         d.ins = [low, P.View(x.buf, cu, 1, x.C - cu)]
+        d.extra = P.upcat_effective_weights(d.w[:, :cu])      # low-res stencil weights per output row/column class
         pl.ops.remove(u)
 
 

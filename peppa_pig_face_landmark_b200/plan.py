@@ -87,6 +87,7 @@ class Op:
         self.flags, self.ints, self.floats, self.name = flags, list(ints), list(floats), name
         self.w_off = self.b_off = -1
         self.w2 = None                       # FLAG_TC: lo-plane weight matrix; its blob offset goes to ints[2]
+        self.extra = None                    # op-specific float32 table; its blob offset goes to ints[0] (OP_UPCAT_DW)
 
     def __repr__(self):
         return "%s %s -> %s act=%d k=%s s=%s d=%s %s" % (OP_NAMES[self.type], self.ins, self.outs,
@@ -144,6 +145,8 @@ class Plan:
             else:
                 op.w_off = put(op.w) if op.w is not None else -1
             op.b_off = put(op.b) if op.b is not None else -1
+            if op.extra is not None:
+                op.ints = [put(op.extra)] + list(op.ints[1:])
         return np.concatenate(parts) if parts else np.zeros(4, np.float32)
 
     def serialize(self):
@@ -259,3 +262,25 @@ def pack_tc_weights(w_ockk, n_tile, n_tiles):
     m = m.reshape(rows, kh * kw * cch * TC_BK)
     hi, lo = split_fp16(m)
     return hi, lo, float(2.0 ** (-s_exp))
+
+
+def upcat_effective_weights(w9c):
+    """Depthwise 3x3 over a bilinear x2 (half_pixel) up-sampled map == a 3x3 stencil on the LOW-res map whose
+    weights depend only on the output pixel's row/column class.  w9c: [9][C] (ky*3+kx major) ->
+    [4][4][3][3][C] float32 indexed (class_y, class_x, a, b): out[y][x] = bias + sum_ab W[cy][cx][a][b] *
+    low[clamp(y//2 + a - 1)][clamp(x//2 + b - 1)].  Classes: 0 = first row/col (the conv's zero padding removes
+    tap 0), 1 = even, 2 = odd, 3 = last row/col (tap 2 removed).  Per dimension U[2m] = .25 L[m-1] + .75 L[m],
+    U[2m+1] = .75 L[m] + .25 L[m+1] with edge-clamped indices (model.py:176 F.interpolate(scale_factor=2,
+    mode='bilinear'); csrc/dw_tma.cu upcat_eff_kernel)."""
+    E = np.array([[.75, .25, 0], [.25, .75, 0], [0, .75, .25]])
+    O = np.array([[.25, .75, 0], [0, .75, .25], [0, .25, .75]])
+    E0, O1 = E.copy(), O.copy()
+    E0[0] = 0
+    O1[2] = 0
+    R = [E0, E, O, O1]
+    w = np.asarray(w9c, np.float64).reshape(3, 3, -1)
+    out = np.zeros((4, 4, 3, 3, w.shape[-1]))
+    for cy in range(4):
+        for cx in range(4):
+            out[cy, cx] = np.einsum("ykc,ya,kb->abc", w, R[cy], R[cx])
+    return np.ascontiguousarray(out.astype(np.float32))
