@@ -11,6 +11,7 @@
 // dwconv_kernel: bias first, then taps in (ky,kx) order with fmaf.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "dw_tma.h"
@@ -138,6 +139,139 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     }
 }
 
+
+// Persistent, double-buffered variant: one CTA walks tiles t = blockIdx.x, += gridDim.x over
+// (image, channel chunk, spatial tile) and the TMA box of tile k+1 is in flight while tile k is computed,
+// so the load latency that the one-tile-per-CTA kernel exposes on every tile is hidden.
+template <int K, int S, int D, bool SPLIT_IN>
+__global__ void __launch_bounds__(DW_THREADS)
+dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const DwTmaK p) {
+    constexpr int CB = SPLIT_IN ? 64 : 32;
+    constexpr int CG = CB / 4;
+    constexpr int PGS = DW_THREADS / CG;
+    constexpr int PX = TH * TW / PGS;
+    constexpr int IH = (TH - 1) * S + (K - 1) * D + 1, IW = (TW - 1) * S + (K - 1) * D + 1;
+    constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
+    constexpr int ROW_BYTES = 128;
+    constexpr int PLANE_BYTES = IH * IW * ROW_BYTES;
+    constexpr int BUF_BYTES = SPLIT_IN ? 2 * PLANE_BYTES : PLANE_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.Wo + TW - 1) / TW;
+    const int tiles_img = tiles_x * ((p.Ho + TH - 1) / TH);
+    const int total = tiles_img * p.chunks * p.batch;
+    const uint32_t sbase = (dsmem_u32(smem) + 127u) & ~127u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int t, int b) {
+        const int sp = t % tiles_img, rest = t / tiles_img;
+        const int chunk = rest % p.chunks, n = rest / p.chunks + p.img0;
+        const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
+        const uint32_t bar_a = dsmem_u32(&bar[b]), dst = sbase + (uint32_t)b * BUF_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)BUF_BYTES) : "memory");
+        const int cx = tx * TW * S - p.pad, cy = ty * TH * S - p.pad, cc = chunk * CB;
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(&tm_hi), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
+        if (SPLIT_IN)
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(dst + PLANE_BYTES), "l"(&tm_lo), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
+    };
+    const int cg = tid % CG, pg = tid / CG;
+    constexpr int SEGS = TW / PX;
+    const int row = pg / SEGS, xs = (pg % SEGS) * PX;
+
+    int t = blockIdx.x;
+    if (tid == 0 && t < total) issue(t, 0);
+    for (int k = 0; t < total; ++k, t += gridDim.x) {
+        const int b = k & 1;
+        if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, b ^ 1);     // buffer b^1 was released by the barrier below
+        {
+            const uint32_t bar_a = dsmem_u32(&bar[b]), parity = (uint32_t)(k >> 1) & 1u;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "DWP_WAIT:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@p bra DWP_DONE;\n\t"
+                "bra DWP_WAIT;\n\t"
+                "DWP_DONE:\n\t"
+                "}\n" ::"r"(bar_a), "r"(parity) : "memory");
+        }
+        const int sp = t % tiles_img, rest = t / tiles_img;
+        const int chunk = rest % p.chunks, n = rest / p.chunks + p.img0;
+        const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
+        const int oy0 = ty * TH, ox0 = tx * TW;
+        const int c = chunk * CB + cg * 4;
+        const uint8_t* tile = smem + (sbase - dsmem_u32(smem)) + (size_t)b * BUF_BYTES;
+        if (c < p.C) {
+            float4 acc[PX];
+            {
+                const float4 bz = *reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+                for (int q = 0; q < PX; ++q) acc[q] = bz;
+            }
+#pragma unroll
+            for (int ky = 0; ky < K; ++ky) {
+                float4 in[SPAN];
+                const int iy = row * S + ky * D;
+#pragma unroll
+                for (int j = 0; j < SPAN; ++j) {
+                    bool used = false;
+#pragma unroll
+                    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+                        for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == j);
+                    if (!used) continue;
+                    const int off = (iy * IW + xs * S + j) * ROW_BYTES;
+                    if (SPLIT_IN) {
+                        const uint2 a = *reinterpret_cast<const uint2*>(tile + off + cg * 8);
+                        const uint2 bb = *reinterpret_cast<const uint2*>(tile + PLANE_BYTES + off + cg * 8);
+                        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+                        const __half2* b2 = reinterpret_cast<const __half2*>(&bb);
+                        const float2 a01 = __half22float2(a2[0]), a23 = __half22float2(a2[1]);
+                        const float2 b01 = __half22float2(b2[0]), b23 = __half22float2(b2[1]);
+                        in[j] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+                    } else {
+                        in[j] = *reinterpret_cast<const float4*>(tile + off + cg * 16);
+                    }
+                }
+#pragma unroll
+                for (int kx = 0; kx < K; ++kx) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.w_ld + c));
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) {
+                        const float4 v = in[q * S + kx * D];
+                        acc[q].x = fmaf(v.x, w.x, acc[q].x);
+                        acc[q].y = fmaf(v.y, w.y, acc[q].y);
+                        acc[q].z = fmaf(v.z, w.z, acc[q].z);
+                        acc[q].w = fmaf(v.w, w.w, acc[q].w);
+                    }
+                }
+            }
+            const int oy = oy0 + row;
+            if (oy < p.Ho) {
+#pragma unroll
+                for (int q = 0; q < PX; ++q) {
+                    const int ox = ox0 + xs + q;
+                    if (ox >= p.Wo) break;
+                    float4 a = acc[q];
+                    a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
+                    a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+                    st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
+                }
+            }
+        }
+        __syncthreads();          // every thread is done reading buffer b before the next iteration refills it
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Up-sampled channels of a DecoderBlock head: out[:, :Cu] = depthwise3x3(bilinear_x2(low)) with the
@@ -397,14 +531,39 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
     return 0;
 }
 
+static int dw_persist_mode() {
+    static int mode = -1;               // SKPS_DW_PERSIST=0: one tile per CTA (the round-1 kernel); default: persistent
+    if (mode < 0) {
+        const char* e = getenv("SKPS_DW_PERSIST");
+        mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return mode;
+}
+
 template <int K, int S, int D, bool SPLIT>
 static int launch_variant(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaStream_t stream) {
     static bool attr_set = false;
+    static int ctas_per_sm = 1, sms = 148;
+    const int buf_bytes = L.smem_bytes - 128;
+    const int persist_smem = 2 * buf_bytes + 128;
     if (!attr_set) {
         SKPS_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SKPS_CUDA(cudaFuncSetAttribute(dw_tma_persist_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       220 * 1024));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        SKPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, dw_tma_persist_kernel<K, S, D, SPLIT>,
+                                                                DW_THREADS, persist_smem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
         attr_set = true;
     }
-    dw_tma_kernel<K, S, D, SPLIT><<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.hi, L.lo, k);
+    const long long total = (long long)grid.x * grid.y * grid.z;
+    if (dw_persist_mode() && total > (long long)sms * ctas_per_sm && persist_smem <= 220 * 1024) {
+        dw_tma_persist_kernel<K, S, D, SPLIT><<<sms * ctas_per_sm, DW_THREADS, persist_smem, stream>>>(L.hi, L.lo, k);
+    } else {
+        dw_tma_kernel<K, S, D, SPLIT><<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.hi, L.lo, k);
+    }
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -412,6 +571,8 @@ static int launch_variant(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaS
 int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream) {
     DwTmaK k = L.k;
     k.img0 = img0;
+    k.chunks = L.chunks;
+    k.batch = batch;
     dim3 grid(((k.Ho + TH - 1) / TH) * ((k.Wo + TW - 1) / TW), L.chunks, batch);
 #define DW_CASE(K_, S_, D_)                                                                              \
     if (L.k_size == K_ && L.stride == S_ && L.dil == D_)                                                 \

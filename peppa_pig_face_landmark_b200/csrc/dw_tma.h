@@ -9,6 +9,7 @@ namespace skps {
 
 struct DwTmaK {
     int C, Ho, Wo, pad, act, img0;
+    int chunks, batch;           // persistent kernel: channel chunks per image, images in this launch
     int w_ld;                    // channel stride of the weight rows (>= C when this layer is a channel slice)
     const float* w; const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff;
