@@ -69,7 +69,21 @@ class PlanInterp:
                 w = torch.from_numpy(op.w).T.reshape(C, 1, op.k[0], op.k[1]).contiguous()
                 y = F.conv2d(x.permute(0, 3, 1, 2), w, torch.from_numpy(op.b), stride=op.s, padding=tuple(op.p),
                              dilation=op.d, groups=C)
-                wr(op.outs[0], _act(y, op.act).permute(0, 2, 3, 1))
+                y = _act(y, op.act).permute(0, 2, 3, 1)
+                wr(op.outs[0], y)
+                if op.flags & P.FLAG_GAP_PARTIAL:
+                    # per-tile channel sums (8x16 output tiles, row-major), as csrc/dw_tma.cu writes them
+                    th, tw = P.DW_TILE_H, P.DW_TILE_W
+                    Ho, Wo = y.shape[1], y.shape[2]
+                    parts = [y[:, a:a + th, b:b + tw].sum(dim=(1, 2)) for a in range(0, Ho, th) for b in range(0, Wo, tw)]
+                    wr(op.outs[1], torch.stack(parts, 1).reshape(N, len(parts), 1, -1))
+            elif t == P.OP_SE_FC:
+                w1, w2 = op.w_ref
+                Cr = op.ints[1]
+                mean = rd(op.ins[0]).sum(dim=(1, 2)) / np.float32(op.ints[3])                 # (N, C)
+                h = _act(mean @ torch.from_numpy(w1).T + torch.from_numpy(op.b[:Cr]), op.act)
+                g = _act(h @ torch.from_numpy(w2).T + torch.from_numpy(op.b[Cr:]), op.ints[2])
+                wr(op.outs[0], g.reshape(N, 1, 1, -1))
             elif t == P.OP_UPCAT_DW:
                 low = rd(op.ins[0]).permute(0, 3, 1, 2)
                 up = F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False)

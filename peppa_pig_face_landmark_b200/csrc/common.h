@@ -11,11 +11,11 @@ namespace skps {
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
-    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14
+    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14, OP_SE_FC = 15
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
-enum { FLAG_IN_U8 = 1, FLAG_TC = 2, FLAG_RES_FIRST = 4 };
+enum { FLAG_IN_U8 = 1, FLAG_TC = 2, FLAG_RES_FIRST = 4, FLAG_GAP_PARTIAL = 8 };
 enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
 
 struct View {            // 6 words
@@ -222,6 +222,9 @@ int launch_det_decode(const TView* heads, const float* consts, const TView& out,
 int launch_scale_ch(const TView& x, const TView& gate, const TView& out, int batch, cudaStream_t s);
 // out = act(sum_j in_j), in_j read at (y >> shift_j, x >> shift_j): HRNet fuse layers (nearest upsample fused)
 int launch_addn(const TView* ins, int n_in, const TView& out, int act, int batch, cudaStream_t s);
+// squeeze-excite gate from the depthwise kernel's per-tile channel sums: mean -> FC -> act1 -> FC -> act2
+int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                 int Cr, int act1, int act2, int hw, int batch, cudaStream_t s);
 int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s);
 
 }  // namespace skps

@@ -23,6 +23,31 @@ __device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)
 constexpr int TH = 8, TW = 16;          // output tile
 constexpr int DW_THREADS = 256;
 
+// Per-tile channel sums of the activated outputs (squeeze-excite: the GlobalAveragePool over this layer's output is
+// assembled from these partial sums by se_fc_kernel, so the tensor is not read again).  Every thread of the CTA calls
+// this with its float4 of per-channel sums (zeros when it owns no valid pixel/channel); fixed summation order.
+template <int CG>
+__device__ __forceinline__ void tile_channel_sums(float4 s, float* __restrict__ dst, bool write_ok) {
+    __shared__ float4 red[DW_THREADS / 32][CG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cg = threadIdx.x % CG;
+#pragma unroll
+    for (int off = 16; off >= CG; off >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+    }
+    if (lane < CG) red[warp][cg] = s;
+    __syncthreads();
+    if (threadIdx.x < CG) {
+        float4 t = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < DW_THREADS / 32; ++w) {
+            const float4 v = red[w][threadIdx.x];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        if (write_ok) *reinterpret_cast<float4*>(dst) = t;
+    }
+}
+
 template <int K, int S, int D, bool SPLIT_IN>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const DwTmaK p) {
@@ -85,6 +110,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             "}\n" ::"r"(bar_a) : "memory");
     }
     const uint8_t* tile = smem + (sbase - dsmem_u32(smem));
+    float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c_ok) {
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
@@ -133,9 +159,15 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                 float4 a = acc[q];
                 a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
                 a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+                psum.x += a.x; psum.y += a.y; psum.z += a.z; psum.w += a.w;
                 st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
             }
         }
+    }
+    if (p.part) {
+        const int cw = chunk * CB + (tid % CG) * 4;          // channel quad written by thread tid < CG
+        tile_channel_sums<CG>(psum, p.part + ((long long)n * gridDim.x + blockIdx.x) * p.part_ld + p.part_coff + cw,
+                              cw < p.C);
     }
 }
 
@@ -211,6 +243,7 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         const int oy0 = ty * TH, ox0 = tx * TW;
         const int c = chunk * CB + cg * 4;
         const uint8_t* tile = smem + (sbase - dsmem_u32(smem)) + (size_t)b * BUF_BYTES;
+        float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < p.C) {
             float4 acc[PX];
             {
@@ -265,11 +298,16 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
                     float4 a = acc[q];
                     a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
                     a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
+                    psum.x += a.x; psum.y += a.y; psum.z += a.z; psum.w += a.w;
                     st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
                 }
             }
         }
-        __syncthreads();          // every thread is done reading buffer b before the next iteration refills it
+        if (p.part) {
+            const int cw = chunk * CB + (tid % CG) * 4;
+            tile_channel_sums<CG>(psum, p.part + ((long long)n * tiles_img + sp) * p.part_ld + p.part_coff + cw, cw < p.C);
+        }
+        __syncthreads();          // every thread is done reading buffer b (and the reduction scratch) before the next iteration
     }
 }
 
@@ -502,7 +540,7 @@ bool dw_tma_supported(const TView& in, const TView& out, int k, int s, int d, in
 }
 
 int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float* w, const float* bias, int k, int s,
-                   int d, int pad, int act, int max_batch) {
+                   int d, int pad, int act, int max_batch, const TView* part) {
     EncodeTiledFn enc = dw_get_encode();
     SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
     SKPS_CHECK(dw_tma_supported(in, out, k, s, d, pad), "dw_tma: unsupported layer");
@@ -525,6 +563,13 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
     kk.C = in.C; kk.Ho = out.H; kk.Wo = out.W; kk.pad = pad; kk.act = act; kk.img0 = 0;
     kk.w = w; kk.bias = bias; kk.w_ld = in.C;
     kk.out = out.base; kk.out_fmt = out.fmt; kk.out_plane = out.plane; kk.out_ld = out.ld; kk.out_coff = out.c_off;
+    kk.part = nullptr; kk.part_ld = 0; kk.part_coff = 0;
+    if (part && part->base) {
+        const int tiles = ((out.H + TH - 1) / TH) * ((out.W + TW - 1) / TW);
+        SKPS_CHECK(part->fmt == DT_F32 && part->c_stride == 1 && part->C == in.C && part->H * part->W == tiles &&
+                   ((part->ld | part->c_off) & 3) == 0, "dw_tma: partial-sum view must be float32 [tiles=%d][C]", tiles);
+        kk.part = (float*)part->base; kk.part_ld = part->ld; kk.part_coff = part->c_off;
+    }
     L.k_size = k; L.stride = s; L.dil = d; L.split = split ? 1 : 0;
     L.chunks = (in.C + CB - 1) / CB;
     L.smem_bytes = IH * IW * 128 * (split ? 2 : 1) + 128;
@@ -619,7 +664,7 @@ int upcat_tma_prepare(UpcatTmaLayer& L, const TView& low, const TView& skip, con
     // skip channels: an ordinary depthwise layer over the channel slice [Cu, Ctot)
     TView o2 = out;
     o2.c_off += low.C; o2.C = skip.C;
-    if (dw_tma_prepare(L.skip, skip, o2, w + low.C, bias + low.C, 3, 1, 1, 1, act, max_batch)) return 1;
+    if (dw_tma_prepare(L.skip, skip, o2, w + low.C, bias + low.C, 3, 1, 1, 1, act, max_batch, nullptr)) return 1;
     L.skip.k.w_ld = Ctot;
     return 0;
 }

@@ -10,6 +10,7 @@ namespace skps {
 struct DwTmaK {
     int C, Ho, Wo, pad, act, img0;
     int chunks, batch;           // persistent kernel: channel chunks per image, images in this launch
+    float* part; int part_ld, part_coff;   // optional [n][tile][C] per-tile channel sums of the outputs (squeeze-excite GAP)
     int w_ld;                    // channel stride of the weight rows (>= C when this layer is a channel slice)
     const float* w; const float* bias;
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff;
@@ -24,7 +25,8 @@ struct DwTmaLayer {
 
 bool dw_tma_supported(const TView& in, const TView& out, int k, int s, int d, int pad);
 int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float* w, const float* bias, int k, int s,
-                   int d, int pad, int act, int max_batch);
+                   int d, int pad, int act, int max_batch, const TView* part = nullptr);
+constexpr int DW_TILE_H = 8, DW_TILE_W = 16;     // output tile of the TMA depthwise kernels (partial-sum rows per image)
 int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream);
 
 // depthwise3x3(concat(bilinear_x2(low), skip)): TMA-staged low-res tiles for the up-sampled channels plus a

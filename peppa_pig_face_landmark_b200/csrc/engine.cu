@@ -137,6 +137,11 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
             case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
+            case OP_SE_FC:
+                // in0 = per-tile channel sums [n][tiles][C]; w = W1^T [C][Cr], i[0] -> W2^T [Cr][C]; b = [b1 (Cr) | b2 (C)]
+                rc = launch_se_fc(in0, out0, w, b, e->d_weights + op.i[0], b + op.i[1], op.i[1], op.act, op.i[2], op.i[3],
+                                  batch, s);
+                break;
             case OP_ADDN: {
                 TView ins[4] = {in0, in1, in2, resolve(e, op.in3, b0)};
                 int n_in = 0;
@@ -288,14 +293,21 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         if (op.type != OP_DWCONV || op.kh != op.kw || op.sh != op.sw || op.dh != op.dw || op.ph != op.pw) continue;
         TView in0 = resolve(e, op.in[0]), out0 = resolve(e, op.out[0]);
         if (!dw_tma_supported(in0, out0, op.kh, op.sh, op.dh, op.ph)) continue;
+        TView part = resolve(e, op.out[1]);          // FLAG_GAP_PARTIAL: per-tile channel sums for the squeeze-excite gate
         if (dw_tma_prepare(e->dwt[i], in0, out0, e->d_weights + op.w_off, e->d_weights + op.b_off, op.kh, op.sh, op.dh,
-                           op.ph, op.act, max_batch)) {
+                           op.ph, op.act, max_batch, (op.flags & FLAG_GAP_PARTIAL) ? &part : nullptr)) {
             char tmp[900];
             snprintf(tmp, sizeof(tmp), "%s", get_error());
             set_error("op %d: %s", i, tmp);
             return fail("dw_tma");
         }
         e->dwt[i].valid = true;
+    }
+    for (int i = 0; i < n_ops; ++i) {
+        if (e->ops[i].type == OP_DWCONV && (e->ops[i].flags & FLAG_GAP_PARTIAL) && !e->dwt[i].valid) {
+            set_error("op %d: per-tile channel sums need the TMA depthwise kernel (SKPS_DW_TMA=0 or unsupported layer)", i);
+            return fail("dw_tma");
+        }
     }
     *out = e;
     return 0;

@@ -810,6 +810,93 @@ int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Squeeze-excite gate in one launch (mobilenetv3 SE of the student encoder, kps_student.onnx
+// .../se/ReduceMean -> conv_reduce -> Relu -> conv_expand -> HardSigmoid):
+//   mean[c]  = (sum over tiles of the depthwise kernel's per-tile channel sums) / (H*W)
+//   hid[j]   = act1(b1[j] + sum_c W1[j][c] * mean[c])
+//   gate[i]  = act2(b2[i] + sum_j W2[i][j] * hid[j])
+// One CTA = 8 samples (they share every weight load); weights are stored transposed ([C][Cr] and [Cr][C]) so the
+// threads of a warp read consecutive floats.  Fixed summation order.
+// ------------------------------------------------------------------------------------------
+constexpr int SE_SAMPLES = 8;
+struct SeFcK {
+    const float* part; int part_ld, part_coff, tiles; float hw;
+    const float* w1t; const float* b1; const float* w2t; const float* b2;    // [C][Cr], [Cr], [Cr][C], [C]
+    float* gate; int gate_ld, gate_coff;
+    int C, Cr, act1, act2, batch;
+};
+
+__global__ void __launch_bounds__(256) se_fc_kernel(const SeFcK p) {
+    extern __shared__ __align__(16) float se_smem[];
+    float* mean = se_smem;                         // [C][8]
+    float* hid = se_smem + (size_t)p.C * SE_SAMPLES;     // [Cr][8]
+    const int n0 = blockIdx.x * SE_SAMPLES;
+    for (int i = threadIdx.x; i < p.C * SE_SAMPLES; i += blockDim.x) {
+        const int m = i / p.C, c = i - m * p.C;    // consecutive threads -> consecutive channels of one sample
+        float sum = 0.f;
+        if (n0 + m < p.batch) {
+            const float* src = p.part + (long long)(n0 + m) * p.tiles * p.part_ld + p.part_coff + c;
+            for (int t = 0; t < p.tiles; ++t) sum += src[(long long)t * p.part_ld];
+        }
+        mean[c * SE_SAMPLES + m] = sum / p.hw;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < p.Cr; j += blockDim.x) {
+        float acc[SE_SAMPLES];
+        const float b = p.b1 ? p.b1[j] : 0.f;
+#pragma unroll
+        for (int m = 0; m < SE_SAMPLES; ++m) acc[m] = b;
+        for (int c = 0; c < p.C; ++c) {
+            const float w = __ldg(p.w1t + (long long)c * p.Cr + j);
+            const float4 a = *reinterpret_cast<const float4*>(mean + c * SE_SAMPLES);
+            const float4 d = *reinterpret_cast<const float4*>(mean + c * SE_SAMPLES + 4);
+            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+            acc[4] = fmaf(d.x, w, acc[4]); acc[5] = fmaf(d.y, w, acc[5]); acc[6] = fmaf(d.z, w, acc[6]); acc[7] = fmaf(d.w, w, acc[7]);
+        }
+#pragma unroll
+        for (int m = 0; m < SE_SAMPLES; ++m) hid[j * SE_SAMPLES + m] = apply_act(acc[m], p.act1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
+        float acc[SE_SAMPLES];
+        const float b = p.b2 ? p.b2[i] : 0.f;
+#pragma unroll
+        for (int m = 0; m < SE_SAMPLES; ++m) acc[m] = b;
+        for (int j = 0; j < p.Cr; ++j) {
+            const float w = __ldg(p.w2t + (long long)j * p.C + i);
+            const float4 a = *reinterpret_cast<const float4*>(hid + j * SE_SAMPLES);
+            const float4 d = *reinterpret_cast<const float4*>(hid + j * SE_SAMPLES + 4);
+            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+            acc[4] = fmaf(d.x, w, acc[4]); acc[5] = fmaf(d.y, w, acc[5]); acc[6] = fmaf(d.z, w, acc[6]); acc[7] = fmaf(d.w, w, acc[7]);
+        }
+#pragma unroll
+        for (int m = 0; m < SE_SAMPLES; ++m)
+            if (n0 + m < p.batch) p.gate[(long long)(n0 + m) * p.gate_ld + p.gate_coff + i] = apply_act(acc[m], p.act2);
+    }
+}
+
+int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                 int Cr, int act1, int act2, int hw, int batch, cudaStream_t s) {
+    SKPS_CHECK(part.fmt == DT_F32 && gate.fmt == DT_F32 && part.c_stride == 1 && gate.c_stride == 1 && part.C == gate.C &&
+               gate.H * gate.W == 1, "se_fc: views");
+    SeFcK k;
+    k.part = (const float*)part.base; k.part_ld = part.ld; k.part_coff = part.c_off; k.tiles = part.H * part.W; k.hw = (float)hw;
+    k.w1t = w1t; k.b1 = b1; k.w2t = w2t; k.b2 = b2;
+    k.gate = (float*)gate.base; k.gate_ld = gate.ld; k.gate_coff = gate.c_off;
+    k.C = part.C; k.Cr = Cr; k.act1 = act1; k.act2 = act2; k.batch = batch;
+    const size_t smem = (size_t)(k.C + k.Cr) * SE_SAMPLES * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKPS_CUDA(cudaFuncSetAttribute(se_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    SKPS_CHECK(smem <= 96 * 1024, "se_fc: %d + %d channels do not fit shared memory", k.C, k.Cr);
+    se_fc_kernel<<<(batch + SE_SAMPLES - 1) / SE_SAMPLES, 256, smem, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // yolov5-face Detect decode (yolov5n-0.5.onnx nodes 502-820): three head tensors (N,H,W,48) ->
 // (N, rows, 16) = [cx,cy,w,h,obj, 5x(lx,ly), cls], rows ordered scale, anchor, y, x.
 // consts: per scale [stride, aw0,ah0, aw1,ah1, aw2,ah2].

@@ -788,6 +788,69 @@ def _fuse_upsample_concat_dw(pl):
         pl.ops.remove(u)
 
 
+def _dw_tma_ok(op):
+    """Mirror of csrc/dw_tma.cu dw_tma_supported(): layers the TMA-staged depthwise kernel takes."""
+    k, s, d, p = op.k, op.s, op.d, op.p
+    if k[0] != k[1] or s[0] != s[1] or d[0] != d[1] or p[0] != p[1]:
+        return False
+    if (k[0], s[0], d[0]) not in ((3, 1, 1), (3, 2, 1), (5, 1, 1), (5, 2, 1), (5, 1, 2)) or p[0] != d[0] * (k[0] - 1) // 2:
+        return False
+    x, o = op.ins[0], op.outs[0]
+    if x.c_stride != 1 or o.c_stride != 1 or x.C != o.C or x.buf.dtype == P.DT_U8:
+        return False
+    return not ((x.C | x.buf.C | x.c_off | o.buf.C | o.c_off) & 7)
+
+
+def _fuse_se_chain(pl):
+    """depthwise -> GlobalAveragePool -> 1x1 (+Relu) -> 1x1 (+HardSigmoid): the pooling pass over the depthwise output
+    disappears (the depthwise kernel writes per-tile channel sums, FLAG_GAP_PARTIAL) and the two tiny FCs become one
+    OP_SE_FC launch.  mobilenetv3 squeeze-excite blocks of the student encoder (kps_student.onnx .../se/*)."""
+    def same(a, b):
+        return a is not None and b is not None and a.buf is b.buf and (a.c_off, a.c_stride, a.C) == (b.c_off, b.c_stride, b.C)
+
+    def readers(v, skip):
+        return [o for o in pl.ops if o not in skip and any(same(i, v) for i in o.ins)]
+
+    for gap in list(pl.ops):
+        if gap.type != P.OP_GAP:
+            continue
+        i = pl.ops.index(gap)
+        dws = [o for o in pl.ops[:i] if o.type == P.OP_DWCONV and same(o.outs[0], gap.ins[0])]
+        if len(dws) != 1 or not _dw_tma_ok(dws[0]) or len(dws[0].outs) != 1:
+            continue
+        dw = dws[0]
+        fc1 = readers(gap.outs[0], [gap])
+        if len(fc1) != 1 or fc1[0].type != P.OP_CONV or list(fc1[0].k) != [1, 1] or (fc1[0].flags & P.FLAG_TC) \
+                or fc1[0].ins[1] is not None or fc1[0].ins[2] is not None:
+            continue
+        fc1 = fc1[0]
+        fc2 = readers(fc1.outs[0], [fc1])
+        if len(fc2) != 1 or fc2[0].type != P.OP_CONV or list(fc2[0].k) != [1, 1] or (fc2[0].flags & P.FLAG_TC) \
+                or fc2[0].ins[1] is not None or fc2[0].ins[2] is not None:
+            continue
+        fc2 = fc2[0]
+        C, Cr = dw.outs[0].C, fc1.outs[0].C
+        if fc2.outs[0].C != C or fc1.ins[0].C != C or (C + Cr) * 8 * 4 > 96 * 1024 or C % 4:
+            continue
+        o = dw.outs[0]
+        tiles = -(-o.H // P.DW_TILE_H) * -(-o.W // P.DW_TILE_W)
+        pb = pl.new_buf(C, tiles, 1, P.DT_F32, dw.name + ":tile_sums")
+        pv = P.View(pb, 0, 1, C)
+        dw.outs = [dw.outs[0], pv]
+        dw.flags |= P.FLAG_GAP_PARTIAL
+        w1 = fc1.w_ref.reshape(Cr, C)                    # [Cout][1][1][Cin]
+        w2 = fc2.w_ref.reshape(C, Cr)
+        b1 = fc1.b if fc1.b is not None else np.zeros(Cr, np.float32)
+        b2 = fc2.b if fc2.b is not None else np.zeros(C, np.float32)
+        se = P.Op(P.OP_SE_FC, [pv], [fc2.outs[0]], fc1.act, w=np.ascontiguousarray(w1.T),
+                  b=np.concatenate([b1, b2]).astype(np.float32), ints=[0, Cr, fc2.act, o.H * o.W], name=fc1.name + ":se_fc")
+        se.extra = np.ascontiguousarray(w2.T)
+        se.w_ref = (w1, w2)
+        pl.ops[pl.ops.index(fc2)] = se
+        pl.ops.remove(fc1)
+        pl.ops.remove(gap)
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -796,6 +859,8 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     lw.analyse()
     lw.emit()
     _fuse_upsample_concat_dw(lw.plan)
+    if os.environ.get("SKPS_SE_FUSE", "1") != "0":
+        _fuse_se_chain(lw.plan)
     chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
     if chunk_env not in ("0", ""):
         lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)

@@ -29,6 +29,7 @@ OP_HM_DECODE = 11     # heat-map argmax + offset decode -> (N,196),(N,98)
 OP_SCALE_CH = 12      # x * gate[n,c]  (squeeze-excite applied ahead of a tensor-core conv)
 OP_UPCAT_DW = 13      # depthwise3x3(concat(bilinear_x2(low), skip)) without materialising the up-sampled tensor
 OP_ADDN = 14          # act(sum of up to 4 inputs), each optionally nearest-upsampled by 2^k (HRNet fuse layers)
+OP_SE_FC = 15         # squeeze-excite gate: per-tile channel sums -> mean -> 1x1 -> act -> 1x1 -> act  (N,1,1,C)
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
 
@@ -97,6 +98,8 @@ class Op:
 FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
 FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo matrix (float16 bytes in the blob)
 FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
+FLAG_GAP_PARTIAL = 8  # depthwise conv also writes per-tile channel sums of its output to outs[1] ([tiles][C] per sample)
+DW_TILE_H, DW_TILE_W = 8, 16     # output tile of csrc/dw_tma.cu (rows of the partial-sum buffer per sample)
 
 
 class Plan:
