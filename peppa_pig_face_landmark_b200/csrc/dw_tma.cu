@@ -186,7 +186,9 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
     constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
     constexpr int ROW_BYTES = 128;
     constexpr int PLANE_BYTES = IH * IW * ROW_BYTES;
-    constexpr int BUF_BYTES = SPLIT_IN ? 2 * PLANE_BYTES : PLANE_BYTES;
+    constexpr int TILE_BYTES = SPLIT_IN ? 2 * PLANE_BYTES : PLANE_BYTES;
+    constexpr int W_BYTES = K * K * CB * 4;                 // this chunk's weights [tap][CB], prefetched with the tile
+    constexpr int BUF_BYTES = TILE_BYTES + W_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar[2];
 
@@ -208,6 +210,13 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
         const uint32_t bar_a = dsmem_u32(&bar[b]), dst = sbase + (uint32_t)b * BUF_BYTES;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)BUF_BYTES) : "memory");
         const int cx = tx * TW * S - p.pad, cy = ty * TH * S - p.pad, cc = chunk * CB;
+        // weights of this channel chunk: one 1-D bulk copy per tap (the ncu profile of the LDG version showed the FMAs
+        // stalled on the weight loads: long-scoreboard 45 % of the samples)
+#pragma unroll 1
+        for (int tap = 0; tap < K * K; ++tap)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + (uint32_t)TILE_BYTES + (uint32_t)tap * CB * 4), "l"(p.w + (size_t)tap * p.w_ld + cc),
+                           "r"((uint32_t)(CB * 4)), "r"(bar_a) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
             ::"r"(dst), "l"(&tm_hi), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
@@ -278,7 +287,7 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
                 }
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.w_ld + c));
+                    const float4 w = *reinterpret_cast<const float4*>(tile + TILE_BYTES + ((ky * K + kx) * CB + cg * 4) * 4);
 #pragma unroll
                     for (int q = 0; q < PX; ++q) {
                         const float4 v = in[q * S + kx * D];
@@ -589,7 +598,7 @@ template <int K, int S, int D, bool SPLIT>
 static int launch_variant(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaStream_t stream) {
     static bool attr_set = false;
     static int ctas_per_sm = 1, sms = 148;
-    const int buf_bytes = L.smem_bytes - 128;
+    const int buf_bytes = L.smem_bytes - 128 + K * K * (SPLIT ? 64 : 32) * 4;      // tile + this chunk's weights
     const int persist_smem = 2 * buf_bytes + 128;
     if (!attr_set) {
         SKPS_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -150,7 +150,10 @@ class Plan:
             op.b_off = put(op.b) if op.b is not None else -1
             if op.extra is not None:
                 op.ints = [put(op.extra)] + list(op.ints[1:])
-        return np.concatenate(parts) if parts else np.zeros(4, np.float32)
+        # tail padding: the depthwise kernels prefetch whole 64-channel weight rows (csrc/dw_tma.cu), which may run a few
+        # floats past a row whose channel count is not a multiple of 64
+        parts.append(np.zeros(256, np.float32))
+        return np.concatenate(parts)
 
     def serialize(self):
         blob = self.pack_weights()
