@@ -110,6 +110,13 @@ SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, c
                                  float out_scale, const float* residual, int out_split, float* out, int stride,
                                  int res_first, int max_batch);
 
+/* Unit-test entry for the few-channel 3x3 convolution kernel (csrc/conv_mma.cu; Cin == Cout == C in {24, 40}, the
+ * Teacher's HRNet branch convs): x, residual, out float32 NHWC; w_packed float16 [tap][hi/lo][C][C] as packed by
+ * plan.pack_mma_weights. */
+SKPS_API int skps_debug_conv_mma(const float* x, int N, int H, int W, int C, const void* w_packed, const float* bias,
+                                 int act, float out_scale, const float* residual, int res_first, int out_split,
+                                 float* out);
+
 /* ------------------------------------------------------------------ image kernels */
 
 /* FaceDetector.preprocess (face_detector.py:45-71): BGR->RGB, cv2.resize INTER_LINEAR

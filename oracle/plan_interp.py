@@ -132,7 +132,10 @@ class PlanInterp:
             elif t == P.OP_DET_DECODE:
                 wr(op.outs[0], self._det_decode(op, [rd(v) for v in op.ins], N))
             elif t == P.OP_HM_DECODE:
-                xy, sc = self._hm_decode(rd(op.ins[0]), op.ints[0])
+                if len(op.ins) > 1 and op.ins[1] is not None:
+                    xy, sc = self._hm_decode_split(rd(op.ins[0]), rd(op.ins[1]), op.w, op.b, op.ints[0])
+                else:
+                    xy, sc = self._hm_decode(rd(op.ins[0]), op.ints[0])
                 wr(op.outs[0], xy.reshape(N, 1, 1, -1))
                 wr(op.outs[1], sc.reshape(N, 1, 1, -1))
             else:
@@ -164,6 +167,25 @@ class PlanInterp:
             parts.append(sg[..., 15:16])
             rows.append(torch.cat(parts, -1).reshape(N, -1, 16))
         return torch.cat(rows, 1).reshape(N, -1, 1, 16)
+
+    @staticmethod
+    def _hm_decode_split(score_map, feat, w_off, b_off, npts):
+        """Score maps only; the x/y offsets are the 1x1 conv rows npts..3*npts evaluated at the arg-max pixel."""
+        N, H, W, C = score_map.shape
+        flat = score_map.reshape(N, H * W, C)[..., :npts]
+        m = flat.max(dim=1, keepdim=True).values
+        ar = torch.arange(H * W).reshape(1, -1, 1)
+        idx = torch.where(flat == m, ar, torch.full_like(ar, H * W)).min(dim=1).values     # N,npts
+        sc = torch.gather(flat, 1, idx[:, None, :])[:, 0]
+        f = feat.reshape(N, H * W, -1)
+        fa = torch.gather(f, 1, idx[:, :, None].expand(N, npts, f.shape[-1]))               # N,npts,K
+        wo = torch.from_numpy(w_off)
+        bo = torch.from_numpy(b_off)
+        ox = (fa * wo[:npts][None]).sum(-1) + bo[:npts]
+        oy = (fa * wo[npts:][None]).sum(-1) + bo[npts:]
+        x = ((idx % W).to(torch.float32) + ox) / np.float32(W)
+        y = ((idx // W).to(torch.float32) + oy) / np.float32(W)
+        return torch.stack([x, y], -1), sc
 
     @staticmethod
     def _hm_decode(hm, npts):

@@ -586,10 +586,14 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
 }
 
 static int dw_persist_mode() {
-    static int mode = -1;               // SKPS_DW_PERSIST=0: one tile per CTA (the round-1 kernel); default: persistent
+    // SKPS_DW_PERSIST=1: persistent double-buffered variant.  Measured on B200 (student, batch 256) it is no faster than
+    // one tile per CTA (8.96 vs 8.96 ms per step; dilated 5x5 layer 236 vs 224 us): these kernels are bound by
+    // shared-memory bandwidth (85 LDS.128 per 400 FMAs), not by the tile load latency, and the second buffer halves
+    // the resident CTAs.  Default: one tile per CTA.
+    static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("SKPS_DW_PERSIST");
-        mode = (e && e[0] == '0') ? 0 : 1;
+        mode = (e && e[0] == '1') ? 1 : 0;
     }
     return mode;
 }

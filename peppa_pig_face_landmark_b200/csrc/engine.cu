@@ -12,6 +12,7 @@
 
 #include "../../include/skps_b200.h"
 #include "common.h"
+#include "conv_mma.h"
 #include "conv_tc.h"
 #include "dw_tma.h"
 
@@ -48,6 +49,7 @@ struct skps_engine {
     bool use_graph = true;
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
+    std::vector<ConvMmaLayer> mma;        // per op; valid where ops[i].flags & FLAG_MMA
     std::vector<DwTmaLayer> dwt;          // per op; TMA-staged depthwise layers (valid flag)
     std::vector<UpcatTmaLayer> upt;       // per op; TMA-staged fused upsample+concat+depthwise
     bool use_dw_tma = true;
@@ -102,6 +104,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
         int rc = 0;
         switch (op.type) {
             case OP_CONV: {
+                if (op.flags & FLAG_MMA) {
+                    rc = conv_mma_launch(e->mma[i], batch, b0, s);
+                    break;
+                }
                 if (op.flags & FLAG_TC) {
                     rc = tc_launch(e->tc[i], batch, b0, e->num_sms, s);
                     break;
@@ -158,7 +164,7 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);
                 break;
             }
-            case OP_HM_DECODE: rc = launch_hm_decode(in0, out0, out1, op.i[0], batch, s); break;
+            case OP_HM_DECODE: rc = launch_hm_decode(in0, in1, w, b, out0, out1, op.i[0], batch, s); break;
             default: set_error("engine: unknown op type %d (op %zu)", op.type, i); return 1;
         }
         if (rc) {
@@ -237,6 +243,20 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
     }
     cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, device);
     // tensor-core conv layers: TMA descriptors over the (fixed) activation buffers and weight matrices
+    e->mma.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const OpDesc& op = e->ops[i];
+        if (op.type != OP_CONV || !(op.flags & FLAG_MMA)) continue;
+        TView in0 = resolve(e, op.in[0]), res = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
+        if (!conv_mma_supported(in0.C, out0.C, op.kh, op.kw, op.sh, op.dh, op.ph) ||
+            conv_mma_prepare(e->mma[i], in0, out0, res, (op.flags & FLAG_RES_FIRST) ? 1 : 0, e->d_weights + op.w_off,
+                             op.b_off >= 0 ? e->d_weights + op.b_off : nullptr, op.f[0], op.act, max_batch)) {
+            char tmp[900];
+            snprintf(tmp, sizeof(tmp), "%s", get_error());
+            set_error("op %d: conv_mma: %s", i, tmp);
+            return fail("mma");
+        }
+    }
     e->tc.resize(n_ops);
     for (int i = 0; i < n_ops; ++i) {
         const OpDesc& op = e->ops[i];

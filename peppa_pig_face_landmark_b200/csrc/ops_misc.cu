@@ -818,18 +818,25 @@ int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s) {
 // One CTA = 8 samples (they share every weight load); weights are stored transposed ([C][Cr] and [Cr][C]) so the
 // threads of a warp read consecutive floats.  Fixed summation order.
 // ------------------------------------------------------------------------------------------
-constexpr int SE_SAMPLES = 8;
+constexpr int SE_SAMPLES = 4;
+constexpr int SE_THREADS = 1024;
 struct SeFcK {
     const float* part; int part_ld, part_coff, tiles; float hw;
     const float* w1t; const float* b1; const float* w2t; const float* b2;    // [C][Cr], [Cr], [Cr][C], [C]
     float* gate; int gate_ld, gate_coff;
     int C, Cr, act1, act2, batch;
+    int jp, slices;              // FC1: threads = slices x jp (jp = Cr rounded up to 32); every slice walks C / slices channels
 };
 
-__global__ void __launch_bounds__(256) se_fc_kernel(const SeFcK p) {
+// One CTA = 4 samples (they share every weight load), 1024 threads.  FC1 is split over `slices` thread groups that
+// each walk a strided share of the C inputs (8 independent weight loads in flight per thread), partials are reduced in
+// slice order; FC2: one thread per output channel.  (The first version -- 32 CTAs, one serial C-long loop per thread --
+// was pure L2 latency: 250 us per launch.)
+__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const SeFcK p) {
     extern __shared__ __align__(16) float se_smem[];
-    float* mean = se_smem;                         // [C][8]
-    float* hid = se_smem + (size_t)p.C * SE_SAMPLES;     // [Cr][8]
+    float4* mean = reinterpret_cast<float4*>(se_smem);                       // [C]       (x,y,z,w = the 4 samples)
+    float4* hid = mean + p.C;                                                // [Cr]
+    float4* part1 = hid + p.Cr;                                              // [slices][jp]
     const int n0 = blockIdx.x * SE_SAMPLES;
     for (int i = threadIdx.x; i < p.C * SE_SAMPLES; i += blockDim.x) {
         const int m = i / p.C, c = i - m * p.C;    // consecutive threads -> consecutive channels of one sample
@@ -838,40 +845,48 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const SeFcK p) {
             const float* src = p.part + (long long)(n0 + m) * p.tiles * p.part_ld + p.part_coff + c;
             for (int t = 0; t < p.tiles; ++t) sum += src[(long long)t * p.part_ld];
         }
-        mean[c * SE_SAMPLES + m] = sum / p.hw;
+        se_smem[c * SE_SAMPLES + m] = sum / p.hw;
+    }
+    __syncthreads();
+    {
+        const int j = threadIdx.x % p.jp, sl = threadIdx.x / p.jp;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < p.Cr && sl < p.slices) {
+            const float* wcol = p.w1t + j;
+#pragma unroll 8
+            for (int c = sl; c < p.C; c += p.slices) {
+                const float w = __ldg(wcol + (long long)c * p.Cr);
+                const float4 a = mean[c];
+                acc.x = fmaf(a.x, w, acc.x); acc.y = fmaf(a.y, w, acc.y); acc.z = fmaf(a.z, w, acc.z); acc.w = fmaf(a.w, w, acc.w);
+            }
+        }
+        if (sl < p.slices) part1[sl * p.jp + j] = acc;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < p.Cr; j += blockDim.x) {
-        float acc[SE_SAMPLES];
         const float b = p.b1 ? p.b1[j] : 0.f;
-#pragma unroll
-        for (int m = 0; m < SE_SAMPLES; ++m) acc[m] = b;
-        for (int c = 0; c < p.C; ++c) {
-            const float w = __ldg(p.w1t + (long long)c * p.Cr + j);
-            const float4 a = *reinterpret_cast<const float4*>(mean + c * SE_SAMPLES);
-            const float4 d = *reinterpret_cast<const float4*>(mean + c * SE_SAMPLES + 4);
-            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
-            acc[4] = fmaf(d.x, w, acc[4]); acc[5] = fmaf(d.y, w, acc[5]); acc[6] = fmaf(d.z, w, acc[6]); acc[7] = fmaf(d.w, w, acc[7]);
+        float4 t = make_float4(b, b, b, b);
+        for (int sl = 0; sl < p.slices; ++sl) {
+            const float4 v = part1[sl * p.jp + j];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
         }
-#pragma unroll
-        for (int m = 0; m < SE_SAMPLES; ++m) hid[j * SE_SAMPLES + m] = apply_act(acc[m], p.act1);
+        hid[j] = make_float4(apply_act(t.x, p.act1), apply_act(t.y, p.act1), apply_act(t.z, p.act1), apply_act(t.w, p.act1));
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.C; i += blockDim.x) {
-        float acc[SE_SAMPLES];
         const float b = p.b2 ? p.b2[i] : 0.f;
-#pragma unroll
-        for (int m = 0; m < SE_SAMPLES; ++m) acc[m] = b;
+        float4 acc = make_float4(b, b, b, b);
+        const float* wcol = p.w2t + i;
+#pragma unroll 8
         for (int j = 0; j < p.Cr; ++j) {
-            const float w = __ldg(p.w2t + (long long)j * p.C + i);
-            const float4 a = *reinterpret_cast<const float4*>(hid + j * SE_SAMPLES);
-            const float4 d = *reinterpret_cast<const float4*>(hid + j * SE_SAMPLES + 4);
-            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
-            acc[4] = fmaf(d.x, w, acc[4]); acc[5] = fmaf(d.y, w, acc[5]); acc[6] = fmaf(d.z, w, acc[6]); acc[7] = fmaf(d.w, w, acc[7]);
+            const float w = __ldg(wcol + (long long)j * p.C);
+            const float4 a = hid[j];
+            acc.x = fmaf(a.x, w, acc.x); acc.y = fmaf(a.y, w, acc.y); acc.z = fmaf(a.z, w, acc.z); acc.w = fmaf(a.w, w, acc.w);
         }
+        const float g[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
         for (int m = 0; m < SE_SAMPLES; ++m)
-            if (n0 + m < p.batch) p.gate[(long long)(n0 + m) * p.gate_ld + p.gate_coff + i] = apply_act(acc[m], p.act2);
+            if (n0 + m < p.batch) p.gate[(long long)(n0 + m) * p.gate_ld + p.gate_coff + i] = apply_act(g[m], p.act2);
     }
 }
 
@@ -884,14 +899,18 @@ int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const f
     k.w1t = w1t; k.b1 = b1; k.w2t = w2t; k.b2 = b2;
     k.gate = (float*)gate.base; k.gate_ld = gate.ld; k.gate_coff = gate.c_off;
     k.C = part.C; k.Cr = Cr; k.act1 = act1; k.act2 = act2; k.batch = batch;
-    const size_t smem = (size_t)(k.C + k.Cr) * SE_SAMPLES * sizeof(float);
+    k.jp = (Cr + 31) / 32 * 32;
+    k.slices = SE_THREADS / k.jp;
+    SKPS_CHECK(k.slices >= 1, "se_fc: %d hidden channels", Cr);
+    if (k.slices > 32) k.slices = 32;
+    const size_t smem = (size_t)(k.C + k.Cr + k.slices * k.jp) * SE_SAMPLES * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         SKPS_CUDA(cudaFuncSetAttribute(se_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
     SKPS_CHECK(smem <= 96 * 1024, "se_fc: %d + %d channels do not fit shared memory", k.C, k.Cr);
-    se_fc_kernel<<<(batch + SE_SAMPLES - 1) / SE_SAMPLES, 256, smem, s>>>(k);
+    se_fc_kernel<<<(batch + SE_SAMPLES - 1) / SE_SAMPLES, SE_THREADS, smem, s>>>(k);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -978,8 +997,13 @@ int launch_det_decode(const TView* heads, const float* consts, const TView& out,
 // arg-max over H*W of hm[:, c] (first maximum), score = max, x = (i%W + hm[:,P+c][i]) / W,
 // y = (i/W + hm[:,2P+c][i]) / W.  Block = one sample; 128 channel lanes x 8 position groups.
 // ------------------------------------------------------------------------------------------
+struct HmOff {          // split head: offsets = rows P..3P of the 1x1 head conv, evaluated at the arg-max pixel only
+    const void* feat; int fmt, ld, coff, K; long long plane;     // the head conv's input (N,H,W,K)
+    const float* w; const float* b;                              // [2P][K], [2P]
+};
+
 __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld, int coff, int H, int W, int P,
-                                                         float* xy, int xy_ld, float* score, int sc_ld) {
+                                                         float* xy, int xy_ld, float* score, int sc_ld, const HmOff off) {
     __shared__ float sv[8][128];
     __shared__ int si[8][128];
     const int n = blockIdx.x;
@@ -1005,8 +1029,23 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
             int idx = si[j][c];
             if (idx != 0x7fffffff && (v > best || (v == best && idx < bi))) { best = v; bi = idx; }
         }
-        float ox = base[(long long)bi * ld + P + c];
-        float oy = base[(long long)bi * ld + 2 * P + c];
+        float ox, oy;
+        if (off.feat) {
+            const long long fe = ((long long)n * HW + bi) * off.ld + off.coff;
+            const float* wx = off.w + (long long)c * off.K;
+            const float* wy = off.w + (long long)(P + c) * off.K;
+            ox = off.b[c]; oy = off.b[P + c];
+            for (int k = 0; k < off.K; k += 4) {
+                const float4 a = ld4(off.feat, off.fmt, off.plane, fe + k);
+                const float4 u = __ldg(reinterpret_cast<const float4*>(wx + k));
+                const float4 v = __ldg(reinterpret_cast<const float4*>(wy + k));
+                ox = fmaf(a.x, u.x, ox); ox = fmaf(a.y, u.y, ox); ox = fmaf(a.z, u.z, ox); ox = fmaf(a.w, u.w, ox);
+                oy = fmaf(a.x, v.x, oy); oy = fmaf(a.y, v.y, oy); oy = fmaf(a.z, v.z, oy); oy = fmaf(a.w, v.w, oy);
+            }
+        } else {
+            ox = base[(long long)bi * ld + P + c];
+            oy = base[(long long)bi * ld + 2 * P + c];
+        }
         float x = __fdiv_rn(__fadd_rn((float)(bi % W), ox), (float)W);
         float y = __fdiv_rn(__fadd_rn((float)(bi / W), oy), (float)W);
         xy[(long long)n * xy_ld + 2 * c] = x;
@@ -1015,12 +1054,20 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
     }
 }
 
-int launch_hm_decode(const TView& hm, const TView& xy, const TView& score, int npts, int batch, cudaStream_t s) {
-    SKPS_CHECK(hm.C == 3 * npts && npts <= 128 && hm.c_stride == 1 && hm.H == hm.W && hm.fmt == DT_F32,
-               "hm_decode: shape/format");
+int launch_hm_decode(const TView& hm, const TView& feat, const float* w_off, const float* b_off, const TView& xy,
+                     const TView& score, int npts, int batch, cudaStream_t s) {
+    SKPS_CHECK((hm.C == 3 * npts || (hm.C == npts && feat.base)) && npts <= 128 && hm.c_stride == 1 && hm.H == hm.W &&
+               hm.fmt == DT_F32, "hm_decode: shape/format");
+    HmOff off = {};
+    if (feat.base) {
+        SKPS_CHECK(w_off && b_off && feat.c_stride == 1 && feat.H == hm.H && feat.W == hm.W &&
+                   ((feat.C | feat.ld | feat.c_off) & 3) == 0, "hm_decode: offset-head input view");
+        off.feat = feat.base; off.fmt = feat.fmt; off.ld = feat.ld; off.coff = feat.c_off; off.K = feat.C; off.plane = feat.plane;
+        off.w = w_off; off.b = b_off;
+    }
     dim3 block(128, 8);
     hm_decode_kernel<<<batch, block, 0, s>>>((const float*)hm.base, hm.ld, hm.c_off, hm.H, hm.W, npts,
-                                             (float*)xy.base, xy.ld, (float*)score.base, score.ld);
+                                             (float*)xy.base, xy.ld, (float*)score.base, score.ld, off);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -528,6 +528,18 @@ class _Lowerer:
         if self.det_heads:
             self._emit_det_decode()
 
+    def _mma_eligible(self, xin, out_v, k, s, p, d, flags, gate):
+        """csrc/conv_mma.cu: 3x3 stride-1 'same' convs with Cin == Cout in {24, 40} reading a SPLIT16-able view."""
+        if not self.use_tc or os.environ.get("SKPS_CONV_MMA", "1") == "0" or (flags & P.FLAG_IN_U8) or gate is not None:
+            return False
+        if list(k) != [3, 3] or list(s) != [1, 1] or list(d) != [1, 1] or list(p[:2]) != [1, 1]:
+            return False
+        if xin.C != out_v.C or xin.C not in (24, 40) or xin.buf.dtype == P.DT_U8:
+            return False
+        if xin.c_stride != 1 or out_v.c_stride != 1 or (xin.buf.C | xin.c_off) % 8 or (out_v.buf.C | out_v.c_off) % 2:
+            return False
+        return xin.H >= 8 and xin.W >= 16
+
     def _tc_eligible(self, xin, k, s, p, d, flags, cout=0, gate=None):
         """Shapes csrc/conv_tc.cu handles: stride-1/2 'same' square convs whose 128-pixel output tiles are whole
         image-row blocks (or whole images for maps under 128 pixels), channel windows aligned for TMA
@@ -576,7 +588,17 @@ class _Lowerer:
             groups = a.get("group", 1)
             xin, gate = self._conv_input(ins[0])
             out_t = self.t[f["out"]]
-            # heat-map head: fuse the decode tail instead of materialising the output tensor name
+            hm_split = None
+            if groups == 1 and list(k) == [1, 1] and self._is_hm_head(f["out"]) and gate is None \
+                    and os.environ.get("SKPS_HM_SPLIT", "1") != "0" and w.shape[0] % 3 == 0 and b is not None:
+                # heat-map head (model.py:511-554 postp): only the score maps are needed densely; the x/y offset maps are
+                # read at ONE pixel per landmark (the arg-max), so the conv computes the first third of its channels and the
+                # decode kernel evaluates the two offset dot products at that pixel from the conv's input
+                npts = w.shape[0] // 3
+                hm_split = dict(npts=npts, xin=xin, w=np.ascontiguousarray(w[npts:].reshape(2 * npts, -1)), b=b[npts:].copy())
+                self.macs_unsplit = out_t.H * out_t.W * w.shape[1] * 2 * npts       # algorithmic MACs stay those of the graph
+                w, b = w[:npts], b[:npts]
+                out_t.C = npts
             out_v = self.view(f["out"])
             flags = P.FLAG_RES_FIRST if f.get("res_first") else 0
             if ins[0] == self.input_name and self.input_u8:
@@ -586,7 +608,14 @@ class _Lowerer:
             if groups == 1:
                 wk = np.ascontiguousarray(w.transpose(0, 2, 3, 1))      # [Cout][kh][kw][Cin]
                 res = self.view(f["res"]) if f.get("res") else None
-                if self._tc_eligible(xin, k, s, p, d, flags, out_v.C, gate):
+                if self._mma_eligible(xin, out_v, k, s, p, d, flags, gate):
+                    # few-channel 3x3 (HRNet 18/36-channel branches, padded to 24/40): halo tile fetched once, taps from smem
+                    xin.buf.dtype = P.DT_SPLIT16
+                    packed, out_scale = P.pack_mma_weights(wk)
+                    o = P.Op(P.OP_CONV, [xin, res, None], [out_v], f["act"], k, s, p[:2], d, packed,
+                             b if b is not None else np.zeros(out_v.C, np.float32), flags | P.FLAG_MMA, floats=[out_scale],
+                             name=n.name)
+                elif self._tc_eligible(xin, k, s, p, d, flags, out_v.C, gate):
                     # tcgen05 path (csrc/conv_tc.cu): float16 hi/lo operands, input buffer in SPLIT16 format
                     if gate is not None:
                         # squeeze-excite scale cannot ride on a TMA-fed operand: apply it in its own pass
@@ -616,6 +645,9 @@ class _Lowerer:
                              name=n.name)
                 o.w_ref = wk
                 pl.macs += mc[0] * out_t.H * out_t.W * mc[1] * k[0] * k[1]
+                if hm_split is not None:
+                    pl.macs += self.macs_unsplit
+                    self.hm_split = hm_split
             else:
                 assert groups == w.shape[0] and w.shape[1] == 1 and gate is None and not f.get("res")
                 wk = np.ascontiguousarray(w.reshape(w.shape[0], -1).T)    # [kh*kw][C]
@@ -678,16 +710,19 @@ class _Lowerer:
         raise LoweringError("emit: unsupported %s %s" % (op, n.name))
 
     # ------------------------------------------------------------------ decode tails
+    def _is_hm_head(self, name):
+        us = self.users(name)
+        return bool(us) and len(us) == 3 and all(u.op == "Slice" for u in us) and any(n.op == "ArgMax" for n in self.nodes)
+
     def _maybe_hm_decode(self, name):
         us = self.users(name)
-        if not us or not all(u.op == "Slice" for u in us) or len(us) != 3:
-            return
-        if not any(n.op == "ArgMax" for n in self.nodes):
+        if not self._is_hm_head(name):
             return
         t = self.t[name]
         bounds = sorted(int(np.atleast_1d(self._const_of(u.inputs[1]))[0]) for u in us)
         npts = bounds[1]
-        if bounds != [0, npts, 2 * npts] or t.C != 3 * npts:
+        split = getattr(self, "hm_split", None)
+        if bounds != [0, npts, 2 * npts] or t.C != (npts if split else 3 * npts):
             raise LoweringError("unexpected heat-map slicing %s" % bounds)
         mods = [n for n in self.nodes if n.op == "Mod"]
         side = int(np.asarray(self._const_of(mods[0].inputs[1])).reshape(-1)[0])
@@ -697,7 +732,12 @@ class _Lowerer:
         xy = pl.new_buf(2 * npts, 1, 1, P.DT_F32, "output")
         sc = pl.new_buf(npts, 1, 1, P.DT_F32, "score")
         vxy, vsc = P.View(xy, 0, 1, 2 * npts), P.View(sc, 0, 1, npts)
-        pl.ops.append(P.Op(P.OP_HM_DECODE, [self.view(name)], [vxy, vsc], ints=[npts], name="hm_decode"))
+        if split:
+            xin = split["xin"]
+            pl.ops.append(P.Op(P.OP_HM_DECODE, [self.view(name), xin], [vxy, vsc], w=split["w"], b=split["b"],
+                               ints=[npts, xin.C], name="hm_decode"))
+        else:
+            pl.ops.append(P.Op(P.OP_HM_DECODE, [self.view(name)], [vxy, vsc], ints=[npts], name="hm_decode"))
         # graph outputs are ['output' (1,196), 'score' (1,98)] in that order
         assert len(self.g.outputs) == 2
         pl.outputs = [vxy, vsc]

@@ -98,6 +98,7 @@ class Op:
 FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
 FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo matrix (float16 bytes in the blob)
 FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
+FLAG_MMA = 16         # 3x3 conv with few channels on the halo-tile mma.sync kernel (csrc/conv_mma.cu): w = packed fp16 hi/lo
 FLAG_GAP_PARTIAL = 8  # depthwise conv also writes per-tile channel sums of its output to outs[1] ([tiles][C] per sample)
 DW_TILE_H, DW_TILE_W = 8, 16     # output tile of csrc/dw_tma.cu (rows of the partial-sum buffer per sample)
 
@@ -141,7 +142,9 @@ class Plan:
                 raw = np.concatenate([raw, np.zeros(pad, np.uint8)])
             return put(raw.view(np.float32))
         for op in self.ops:
-            if op.flags & FLAG_TC:
+            if op.flags & FLAG_MMA:
+                op.w_off = put_raw(op.w)
+            elif op.flags & FLAG_TC:
                 op.w_off = put_raw(op.w)
                 lo_off = put_raw(op.w2)
                 op.ints = list(op.ints[:2]) + [lo_off] + list(op.ints[3:])
@@ -290,3 +293,14 @@ def upcat_effective_weights(w9c):
         for cx in range(4):
             out[cy, cx] = np.einsum("ykc,ya,kb->abc", w, R[cy], R[cx])
     return np.ascontiguousarray(out.astype(np.float32))
+
+
+def pack_mma_weights(w_ockk):
+    """[Cout][3][3][Cin] float32 -> (packed, out_scale): float16 array [tap][plane hi/lo][Cout][Cin] for
+    csrc/conv_mma.cu, pre-multiplied by an exact power of two like pack_tc_weights."""
+    cout, kh, kw, cin = w_ockk.shape
+    wmax = float(np.abs(w_ockk).max())
+    s_exp = int(np.floor(np.log2(8192.0 / wmax))) if wmax > 0 else 0
+    w = (w_ockk * np.float32(2.0 ** s_exp)).astype(np.float32)
+    hi, lo = split_fp16(w.transpose(1, 2, 0, 3).reshape(kh * kw, cout, cin))        # [tap][Cout][Cin]
+    return np.ascontiguousarray(np.stack([hi, lo], axis=1)), float(2.0 ** (-s_exp))

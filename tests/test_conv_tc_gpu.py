@@ -97,3 +97,42 @@ def test_conv_tc_small_maps_share_a_tile():
     assert _run(5, 8, 8, 144, 144, 3, 1, 1) < 1e-5                      # odd batch: partial tile, TMA store clips
     assert _run(3, 8, 8, 144, 72, 1, 1, 0, max_batch=8) < 1e-5         # spare capacity: the partial tile lands in unused slots
     assert _run(3, 8, 8, 144, 24, 1, 1, 0, out_split=True, max_batch=4) < 1e-5
+
+
+def _run_mma(N, H, W, C, act, with_res=False, res_first=False, out_split=True, seed=0):
+    """csrc/conv_mma.cu (few-channel 3x3, halo tile + mma.sync) against torch conv2d in float32."""
+    import torch
+    import torch.nn.functional as F
+    from peppa_pig_face_landmark_b200 import plan as P, runtime as rt
+    lib = rt.load_library()
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, H, W, C)).astype(np.float32) * 2
+    w = (rng.standard_normal((C, 3, 3, C)) / np.sqrt(9 * C)).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    res = rng.standard_normal((N, H, W, C)).astype(np.float32) if with_res else None
+    packed, out_scale = P.pack_mma_weights(w)
+    out = np.empty((N, H, W, C), np.float32)
+    rt.check(lib.skps_debug_conv_mma(x.ctypes.data, N, H, W, C, packed.ctypes.data, b.ctypes.data, act, out_scale,
+                                     res.ctypes.data if res is not None else None, 1 if res_first else 0,
+                                     1 if out_split else 0, out.ctypes.data))
+    y = F.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(0, 3, 1, 2).contiguous(),
+                 torch.from_numpy(b), padding=1)
+    if res is not None and res_first:
+        y = y + torch.from_numpy(res).permute(0, 3, 1, 2)
+    if act == 1:
+        y = torch.relu(y)
+    y = y.permute(0, 2, 3, 1).numpy()
+    if res is not None and not res_first:
+        y = y + res
+    err = np.abs(out - y).max() / (np.abs(y).max() + 1e-9)
+    print('conv_mma', (N, H, W, C, act, with_res, res_first, out_split), 'rel err %.3e' % err)
+    return err
+
+
+def test_conv_mma_small_channel_3x3():
+    """HRNet branch convs of the Teacher: 18->24 and 36->40 padded channels, 64x64 / 32x32 maps, odd sizes too."""
+    assert _run_mma(3, 64, 64, 24, 1) < 1e-5
+    assert _run_mma(2, 64, 64, 24, 1, with_res=True, res_first=True) < 1e-5            # BasicBlock conv2: += shortcut, relu
+    assert _run_mma(3, 32, 32, 40, 1, with_res=True, res_first=True, out_split=False) < 1e-5
+    assert _run_mma(2, 32, 32, 40, 0, with_res=True, res_first=False) < 1e-5
+    assert _run_mma(1, 24, 40, 24, 0) < 1e-5                                             # partial tiles in both directions

@@ -11,7 +11,7 @@ echo "== bench (default)" | tee -a $OUT/steps.log
 timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/steps.log
 python -c "
 import json; d=json.load(open('$OUT/bench.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['achieved'], d['roofline']['kernel_ms'])"
-for sw in ${AB_SWITCHES:-"SKPS_DW_PERSIST=0" "SKPS_UPCAT_EFF=1" "SKPS_SE_FUSE=0"}; do
+for sw in ${AB_SWITCHES:-"SKPS_DW_PERSIST=1" "SKPS_HM_SPLIT=0" "SKPS_SE_FUSE=0"}; do
   env $sw timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_$sw.json 2> $OUT/bench_$sw.err
   python -c "
 import json; d=json.load(open('$OUT/bench_$sw.json')); print('$sw', 'value', d['value'], 'ms', d['ms_per_step'])" | tee -a $OUT/steps.log
@@ -19,7 +19,10 @@ done
 echo "== teacher sweep" | tee -a $OUT/steps.log
 timeout 900 python tools/bench_teacher.py --batches ${TEACHER_BATCHES:-1,2,4,8,16,32,64,128,256,512,1024} --steps 5 --out $OUT/teacher_sweep.json > $OUT/teacher_sweep.log 2>&1; echo "teacher rc=$?" | tee -a $OUT/steps.log
 cut -c 1-160 $OUT/teacher_sweep.log
+SKPS_CONV_MMA=0 timeout 600 python tools/bench_teacher.py --batches ${TEACHER_BATCHES:-64,256} --steps 5 > $OUT/teacher_sweep_nomma.log 2>&1; echo "teacher (no conv_mma) rc=$?" | tee -a $OUT/steps.log
+cut -c 1-160 $OUT/teacher_sweep_nomma.log
 echo "== ncu launch lists" | tee -a $OUT/steps.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/teacher_b64_launches.csv python tools/profile_student.py 64 1 teacher > $OUT/ncu_teacher.log 2>&1; echo "ncu teacher rc=$?" | tee -a $OUT/steps.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/student_b256_launches.csv python tools/profile_student.py 256 1 student > $OUT/ncu_student.log 2>&1; echo "ncu student rc=$?" | tee -a $OUT/steps.log
 if [ -n "$NCU_FULL_DW" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"dw_tma|upcat" -c 22 -o $OUT/full_dw python tools/profile_student.py 256 1 student > $OUT/ncu_full_dw.log 2>&1; echo "ncu full dw rc=$?" | tee -a $OUT/steps.log

@@ -30,18 +30,20 @@ def report(which="student", batch=2, out=sys.stdout):
     sess = Session(path)
     worst = 0.0
     rows = []
+    written = {v.buf.idx for op in eng.plan.ops for v in op.outs}      # fusions leave some named tensors unmaterialised
     for n in range(batch):
         xf = x_u8[n].transpose(2, 0, 1).astype(np.float32)[None] / np.float32(255.)
         ref_outs, kept = sess.run(xf, keep="all")
         for b in eng.plan.bufs:
-            if b.name not in kept or b.idx == eng.plan.input.buf.idx:
+            if b.name not in kept or b.idx == eng.plan.input.buf.idx or b.idx not in written:
                 continue
             ref = kept[b.name].numpy()
             if ref.ndim != 4:
                 continue
             got = eng.read_buffer(b.idx, batch)[n]
             ref = ref[0].transpose(1, 2, 0)
-            got = got[..., :ref.shape[-1]]          # buffers may be channel-padded
+            nc = min(ref.shape[-1], b.C)            # buffers may be channel-padded; the split heat-map head keeps only the score maps
+            got, ref = got[..., :nc], ref[..., :nc]
             if got.shape != ref.shape:
                 rows.append((b.idx, b.name, "SHAPE %s vs %s" % (got.shape, ref.shape)))
                 continue
