@@ -73,7 +73,7 @@ class PlanInterp:
                 wr(op.outs[0], y)
                 if op.flags & P.FLAG_GAP_PARTIAL:
                     # per-tile channel sums (8x16 output tiles, row-major), as csrc/dw_tma.cu writes them
-                    th, tw = P.DW_TILE_H, P.DW_TILE_W
+                    th, tw = P.dw_tile_rows(op.k[0], op.s[0]), P.DW_TILE_W
                     Ho, Wo = y.shape[1], y.shape[2]
                     parts = [y[:, a:a + th, b:b + tw].sum(dim=(1, 2)) for a in range(0, Ho, th) for b in range(0, Wo, tw)]
                     wr(op.outs[1], torch.stack(parts, 1).reshape(N, len(parts), 1, -1))

@@ -147,17 +147,23 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     ldsm_x4(arow[h] + a_lane_off + ks * 32, ah[h]);
                     ldsm_x4(arow[h] + PLANE_AL + a_lane_off + ks * 32, al[h]);
                 }
+                // per accumulator the three products are added in the order lo*hi, hi*lo, hi*hi (small terms first); the passes
+                // are issued across all 2*NT accumulators so that consecutive MMAs are independent
+                uint32_t bw[NT][4];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    uint32_t bw[4];
-                    ldsm_x4(wtap + (uint32_t)(j * 8) * PITCH + ks * 32 + b_lane_off, bw);
+                for (int j = 0; j < NT; ++j) ldsm_x4(wtap + (uint32_t)(j * 8) * PITCH + ks * 32 + b_lane_off, bw[j]);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        mma_16816(acc[h][j], al[h], bw[0], bw[1]);        // lo * hi   (small terms first)
-                        mma_16816(acc[h][j], ah[h], bw[2], bw[3]);        // hi * lo
-                        mma_16816(acc[h][j], ah[h], bw[0], bw[1]);        // hi * hi
-                    }
-                }
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_16816(acc[h][j], al[h], bw[j][0], bw[j][1]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_16816(acc[h][j], ah[h], bw[j][2], bw[j][3]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_16816(acc[h][j], ah[h], bw[j][0], bw[j][1]);
             }
             if (K8) {
                 uint32_t ah[2][2], al[2][2];
@@ -166,66 +172,66 @@ conv_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                     ldsm_x2(arow[h] + a_px_off + KS16 * 32, ah[h]);
                     ldsm_x2(arow[h] + PLANE_AL + a_px_off + KS16 * 32, al[h]);
                 }
+                uint32_t bw[NT][2];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    uint32_t bw[2];
-                    ldsm_x2(wtap + (uint32_t)(j * 8) * PITCH + KS16 * 32 + b8_lane_off, bw);
+                for (int j = 0; j < NT; ++j) ldsm_x2(wtap + (uint32_t)(j * 8) * PITCH + KS16 * 32 + b8_lane_off, bw[j]);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        mma_1688(acc[h][j], al[h], bw[0]);
-                        mma_1688(acc[h][j], ah[h], bw[1]);
-                        mma_1688(acc[h][j], ah[h], bw[0]);
-                    }
-                }
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_1688(acc[h][j], al[h], bw[j][0]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_1688(acc[h][j], ah[h], bw[j][1]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) mma_1688(acc[h][j], ah[h], bw[j][0]);
             }
         }
-        // ---- epilogue: thread holds, per (row h, n-tile j): pixels g and g+8 of the row, channels 8j + 2*tq, +1
+        // ---- epilogue: the accumulator fragments (2 channels of 2 pixels per register pair) go through shared memory so that
+        // one thread finishes one pixel x all COUT channels with 16-byte residual loads and stores
+        __syncthreads();                                   // all warps are done with this buffer's halo tile: reuse it as staging
         {
+            float* stage = reinterpret_cast<float*>(smem + (sbase - msmem_u32(smem)) + (size_t)b * BUF);     // [128 px][COUT + 4]
+            constexpr int SP = COUT + 4;                   // row pitch in floats (bank spread for the fragment writes)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+                        *reinterpret_cast<float2*>(stage + ((2 * warp + h) * MT_W + g + 8 * half) * SP + 8 * j + 2 * tq) =
+                            make_float2(acc[h][j][2 * half], acc[h][j][2 * half + 1]);
+            __syncthreads();
             const int n = t / p.tiles_img + p.img0, sp = t % p.tiles_img;
             const int ty = sp / p.tiles_x, tx = sp - ty * p.tiles_x;
+            const int y = ty * MT_H + tid / MT_W, x = tx * MT_W + tid % MT_W;          // thread -> pixel of the tile
+            if (y < p.H && x < p.W) {
+                const long long pix = ((long long)n * p.H + y) * p.W + x;
+                const float* srow = stage + tid * SP;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int y = ty * MT_H + 2 * warp + h;
+                for (int c8 = 0; c8 < COUT; c8 += 8) {
+                    float8 v, r;
+                    const float4 s0 = *reinterpret_cast<const float4*>(srow + c8), s1 = *reinterpret_cast<const float4*>(srow + c8 + 4);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 + 4));
+                    v.v[0] = fmaf(s0.x, p.out_scale, b0.x); v.v[1] = fmaf(s0.y, p.out_scale, b0.y);
+                    v.v[2] = fmaf(s0.z, p.out_scale, b0.z); v.v[3] = fmaf(s0.w, p.out_scale, b0.w);
+                    v.v[4] = fmaf(s1.x, p.out_scale, b1.x); v.v[5] = fmaf(s1.y, p.out_scale, b1.y);
+                    v.v[6] = fmaf(s1.z, p.out_scale, b1.z); v.v[7] = fmaf(s1.w, p.out_scale, b1.w);
+                    if (p.res) r = ld8(p.res, p.res_fmt, p.res_plane, pix * p.res_ld + p.res_coff + c8);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int x = tx * MT_W + g + 8 * half;
-                    if (y >= p.H || x >= p.W) continue;
-                    const long long pix = ((long long)n * p.H + y) * p.W + x;
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const int ch = 8 * j + 2 * tq;
-                        float v0 = fmaf(acc[h][j][2 * half], p.out_scale, p.bias ? __ldg(p.bias + ch) : 0.f);
-                        float v1 = fmaf(acc[h][j][2 * half + 1], p.out_scale, p.bias ? __ldg(p.bias + ch + 1) : 0.f);
-                        float r0 = 0.f, r1 = 0.f;
-                        if (p.res) {
-                            const long long re = pix * p.res_ld + p.res_coff + ch;
-                            if (p.res_fmt == DT_SPLIT16) {
-                                const __half* rh = (const __half*)p.res;
-                                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(rh + re));
-                                const float2 c = __half22float2(*reinterpret_cast<const __half2*>(rh + re + p.res_plane));
-                                r0 = a.x + c.x; r1 = a.y + c.y;
-                            } else {
-                                const float2 a = *reinterpret_cast<const float2*>((const float*)p.res + re);
-                                r0 = a.x; r1 = a.y;
-                            }
-                        }
-                        if (p.res_first) { v0 = apply_act(v0 + r0, p.act); v1 = apply_act(v1 + r1, p.act); }
-                        else { v0 = apply_act(v0, p.act) + r0; v1 = apply_act(v1, p.act) + r1; }
-                        const long long oe = pix * p.out_ld + p.out_coff + ch;
-                        if (p.out_fmt == DT_SPLIT16) {
-                            __half* oh = (__half*)p.out;
-                            const __half2 hi = __floats2half2_rn(v0, v1);
-                            const float2 hf = __half22float2(hi);
-                            *reinterpret_cast<__half2*>(oh + oe) = hi;
-                            *reinterpret_cast<__half2*>(oh + oe + p.out_plane) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                        } else {
-                            *reinterpret_cast<float2*>((float*)p.out + oe) = make_float2(v0, v1);
-                        }
+                    for (int e = 0; e < 8; ++e) {
+                        const float rr = p.res ? r.v[e] : 0.f;
+                        v.v[e] = p.res_first ? apply_act(v.v[e] + rr, p.act) : apply_act(v.v[e], p.act) + rr;
                     }
+                    st8(p.out, p.out_fmt, p.out_plane, pix * p.out_ld + p.out_coff + c8, v);
                 }
             }
         }
-        __syncthreads();          // every warp is done reading buffer b before the next iteration refills it
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes (generic proxy) before the next TMA refill
+        __syncthreads();          // every warp is done with buffer b before the next iteration refills it
     }
 }
 
@@ -255,9 +261,9 @@ int conv_mma_prepare(ConvMmaLayer& L, const TView& in, const TView& out, const T
     SKPS_CHECK(enc, "cuTensorMapEncodeTiled entry point not available");
     SKPS_CHECK(conv_mma_supported(in.C, out.C, 3, 3, 1, 1, 1), "conv_mma: unsupported channels %d -> %d", in.C, out.C);
     SKPS_CHECK(in.fmt == DT_SPLIT16 && in.c_stride == 1 && ((in.ld | in.c_off) & 7) == 0, "conv_mma: input view");
-    SKPS_CHECK(out.c_stride == 1 && ((out.ld | out.c_off) & 1) == 0 && in.H == out.H && in.W == out.W &&
-               (out.fmt == DT_SPLIT16 || out.fmt == DT_F32), "conv_mma: output view");
-    SKPS_CHECK(!res.base || (res.c_stride == 1 && ((res.ld | res.c_off) & 1) == 0 && res.C == out.C), "conv_mma: residual view");
+    SKPS_CHECK(out.c_stride == 1 && ((out.ld | out.c_off) & 7) == 0 && in.H == out.H && in.W == out.W &&
+               (out.fmt == DT_SPLIT16 || out.fmt == DT_F32) && bias, "conv_mma: output view / bias");
+    SKPS_CHECK(!res.base || (res.c_stride == 1 && ((res.ld | res.c_off) & 7) == 0 && res.C == out.C), "conv_mma: residual view");
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)in.ld * 2, (cuuint64_t)in.W * in.ld * 2, (cuuint64_t)in.H * in.W * in.ld * 2};

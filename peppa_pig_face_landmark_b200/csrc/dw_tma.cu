@@ -20,7 +20,7 @@ namespace skps {
 
 __device__ __forceinline__ uint32_t dsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr int TH = 8, TW = 16;          // output tile
+constexpr int TH = 8, TW = 16;          // output tile (TH x RY rows)
 constexpr int DW_THREADS = 256;
 
 // Per-tile channel sums of the activated outputs (squeeze-excite: the GlobalAveragePool over this layer's output is
@@ -48,14 +48,18 @@ __device__ __forceinline__ void tile_channel_sums(float4 s, float* __restrict__ 
     }
 }
 
-template <int K, int S, int D, bool SPLIT_IN>
+// Output rows per thread: the 5x5 stride-1 layers are shared-memory-bandwidth bound (ncu: 85 LDS.128 per 400 FMAs, DRAM
+// at 28 %); a thread that owns rows r and r+D of the same columns re-uses K-1 of the K input rows it loads for the
+// first row, so the tile is 16 rows high for them and the loads per output drop 1.75x.
+template <int K, int S, int D, bool SPLIT_IN, int RY>
 __global__ void __launch_bounds__(DW_THREADS)
 dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const DwTmaK p) {
+    constexpr int THT = TH * RY;                           // tile height in output rows
     constexpr int CB = SPLIT_IN ? 64 : 32;                 // channels per CTA: 128-byte pixel rows in smem
     constexpr int CG = CB / 4;                             // 4-channel groups
     constexpr int PGS = DW_THREADS / CG;                   // pixel groups
-    constexpr int PX = TH * TW / PGS;                      // consecutive output pixels (along x) per thread
-    constexpr int IH = (TH - 1) * S + (K - 1) * D + 1, IW = (TW - 1) * S + (K - 1) * D + 1;
+    constexpr int PX = TH * TW / PGS;                      // consecutive output pixels (along x) per thread and row
+    constexpr int IH = (THT - 1) * S + (K - 1) * D + 1, IW = (TW - 1) * S + (K - 1) * D + 1;
     constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
     constexpr int ROW_BYTES = 128;
     constexpr int PLANE_BYTES = IH * IW * ROW_BYTES;
@@ -67,7 +71,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int chunk = blockIdx.y;
     const int n = blockIdx.z + p.img0;
-    const int oy0 = ty * TH, ox0 = tx * TW;
+    const int oy0 = ty * THT, ox0 = tx * TW;
     const uint32_t sbase = (dsmem_u32(smem) + 127u) & ~127u;
     const uint32_t bar_a = dsmem_u32(&bar);
 
@@ -85,17 +89,20 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                 ::"r"(sbase + PLANE_BYTES), "l"(&tm_lo), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
     }
-    // thread -> (4-channel group, row, x segment)
+    // thread -> (4-channel group, row slot, x segment); row slot pr owns output rows row0 + ry*D (ry < RY)
     const int cg = tid % CG, pg = tid / CG;
     constexpr int SEGS = TW / PX;
-    const int row = pg / SEGS, xs = (pg % SEGS) * PX;
+    const int pr = pg / SEGS, xs = (pg % SEGS) * PX;
+    const int row0 = RY == 1 ? pr : (pr / D) * (RY * D) + (pr % D);
     const int c = chunk * CB + cg * 4;
     const bool c_ok = c < p.C;
-    float4 acc[PX];
+    float4 acc[RY][PX];
     {
         const float4 b = c_ok ? *reinterpret_cast<const float4*>(p.bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < PX; ++q) acc[q] = b;
+        for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+            for (int q = 0; q < PX; ++q) acc[ry][q] = b;
     }
     __syncthreads();        // barrier init visible to all waiters
     {
@@ -112,19 +119,21 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     const uint8_t* tile = smem + (sbase - dsmem_u32(smem));
     float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c_ok) {
+        // input row j (= row0*S + j*D) feeds tap ky = j of output row 0 and tap ky = j-1 of output row 1
+        float4 wprev[K];
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
+        for (int j = 0; j < K + RY - 1; ++j) {
             float4 in[SPAN];
-            const int iy = row * S + ky * D;
+            const int iy = row0 * S + j * D;
 #pragma unroll
-            for (int j = 0; j < SPAN; ++j) {
+            for (int i = 0; i < SPAN; ++i) {
                 bool used = false;
 #pragma unroll
                 for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-                    for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == j);
+                    for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == i);
                 if (!used) continue;
-                const int off = (iy * IW + xs * S + j) * ROW_BYTES;
+                const int off = (iy * IW + xs * S + i) * ROW_BYTES;
                 if (SPLIT_IN) {
                     const uint2 a = *reinterpret_cast<const uint2*>(tile + off + cg * 8);
                     const uint2 b = *reinterpret_cast<const uint2*>(tile + PLANE_BYTES + off + cg * 8);
@@ -132,179 +141,48 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
                     const __half2* b2 = reinterpret_cast<const __half2*>(&b);
                     const float2 a01 = __half22float2(a2[0]), a23 = __half22float2(a2[1]);
                     const float2 b01 = __half22float2(b2[0]), b23 = __half22float2(b2[1]);
-                    in[j] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+                    in[i] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
                 } else {
-                    in[j] = *reinterpret_cast<const float4*>(tile + off + cg * 16);
+                    in[i] = *reinterpret_cast<const float4*>(tile + off + cg * 16);
                 }
             }
 #pragma unroll
             for (int kx = 0; kx < K; ++kx) {
-                const float4 w = *reinterpret_cast<const float4*>(p.w + (ky * K + kx) * p.w_ld + c);
-#pragma unroll
-                for (int q = 0; q < PX; ++q) {
-                    const float4 v = in[q * S + kx * D];
-                    acc[q].x = fmaf(v.x, w.x, acc[q].x);
-                    acc[q].y = fmaf(v.y, w.y, acc[q].y);
-                    acc[q].z = fmaf(v.z, w.z, acc[q].z);
-                    acc[q].w = fmaf(v.w, w.w, acc[q].w);
-                }
-            }
-        }
-        const int oy = oy0 + row;
-        if (oy < p.Ho) {
-#pragma unroll
-            for (int q = 0; q < PX; ++q) {
-                const int ox = ox0 + xs + q;
-                if (ox >= p.Wo) break;
-                float4 a = acc[q];
-                a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
-                a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
-                psum.x += a.x; psum.y += a.y; psum.z += a.z; psum.w += a.w;
-                st4(p.out, p.out_fmt, p.out_plane, (((long long)n * p.Ho + oy) * p.Wo + ox) * p.out_ld + p.out_coff + c, a);
-            }
-        }
-    }
-    if (p.part) {
-        const int cw = chunk * CB + (tid % CG) * 4;          // channel quad written by thread tid < CG
-        tile_channel_sums<CG>(psum, p.part + ((long long)n * gridDim.x + blockIdx.x) * p.part_ld + p.part_coff + cw,
-                              cw < p.C);
-    }
-}
-
-
-// Persistent, double-buffered variant: one CTA walks tiles t = blockIdx.x, += gridDim.x over
-// (image, channel chunk, spatial tile) and the TMA box of tile k+1 is in flight while tile k is computed,
-// so the load latency that the one-tile-per-CTA kernel exposes on every tile is hidden.
-template <int K, int S, int D, bool SPLIT_IN>
-__global__ void __launch_bounds__(DW_THREADS)
-dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const DwTmaK p) {
-    constexpr int CB = SPLIT_IN ? 64 : 32;
-    constexpr int CG = CB / 4;
-    constexpr int PGS = DW_THREADS / CG;
-    constexpr int PX = TH * TW / PGS;
-    constexpr int IH = (TH - 1) * S + (K - 1) * D + 1, IW = (TW - 1) * S + (K - 1) * D + 1;
-    constexpr int SPAN = (PX - 1) * S + (K - 1) * D + 1;
-    constexpr int ROW_BYTES = 128;
-    constexpr int PLANE_BYTES = IH * IW * ROW_BYTES;
-    constexpr int TILE_BYTES = SPLIT_IN ? 2 * PLANE_BYTES : PLANE_BYTES;
-    constexpr int W_BYTES = K * K * CB * 4;                 // this chunk's weights [tap][CB], prefetched with the tile
-    constexpr int BUF_BYTES = TILE_BYTES + W_BYTES;
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar[2];
-
-    const int tid = threadIdx.x;
-    const int tiles_x = (p.Wo + TW - 1) / TW;
-    const int tiles_img = tiles_x * ((p.Ho + TH - 1) / TH);
-    const int total = tiles_img * p.chunks * p.batch;
-    const uint32_t sbase = (dsmem_u32(smem) + 127u) & ~127u;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dsmem_u32(&bar[1])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int t, int b) {
-        const int sp = t % tiles_img, rest = t / tiles_img;
-        const int chunk = rest % p.chunks, n = rest / p.chunks + p.img0;
-        const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
-        const uint32_t bar_a = dsmem_u32(&bar[b]), dst = sbase + (uint32_t)b * BUF_BYTES;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((uint32_t)BUF_BYTES) : "memory");
-        const int cx = tx * TW * S - p.pad, cy = ty * TH * S - p.pad, cc = chunk * CB;
-        // weights of this channel chunk: one 1-D bulk copy per tap (the ncu profile of the LDG version showed the FMAs
-        // stalled on the weight loads: long-scoreboard 45 % of the samples)
-#pragma unroll 1
-        for (int tap = 0; tap < K * K; ++tap)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + (uint32_t)TILE_BYTES + (uint32_t)tap * CB * 4), "l"(p.w + (size_t)tap * p.w_ld + cc),
-                           "r"((uint32_t)(CB * 4)), "r"(bar_a) : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(dst), "l"(&tm_hi), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
-        if (SPLIT_IN)
-            asm volatile(
-                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                ::"r"(dst + PLANE_BYTES), "l"(&tm_lo), "r"(bar_a), "r"(cc), "r"(cx), "r"(cy), "r"(n) : "memory");
-    };
-    const int cg = tid % CG, pg = tid / CG;
-    constexpr int SEGS = TW / PX;
-    const int row = pg / SEGS, xs = (pg % SEGS) * PX;
-
-    int t = blockIdx.x;
-    if (tid == 0 && t < total) issue(t, 0);
-    for (int k = 0; t < total; ++k, t += gridDim.x) {
-        const int b = k & 1;
-        if (tid == 0 && t + (int)gridDim.x < total) issue(t + gridDim.x, b ^ 1);     // buffer b^1 was released by the barrier below
-        {
-            const uint32_t bar_a = dsmem_u32(&bar[b]), parity = (uint32_t)(k >> 1) & 1u;
-            asm volatile(
-                "{\n\t"
-                ".reg .pred p;\n\t"
-                "DWP_WAIT:\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                "@p bra DWP_DONE;\n\t"
-                "bra DWP_WAIT;\n\t"
-                "DWP_DONE:\n\t"
-                "}\n" ::"r"(bar_a), "r"(parity) : "memory");
-        }
-        const int sp = t % tiles_img, rest = t / tiles_img;
-        const int chunk = rest % p.chunks, n = rest / p.chunks + p.img0;
-        const int ty = sp / tiles_x, tx = sp - ty * tiles_x;
-        const int oy0 = ty * TH, ox0 = tx * TW;
-        const int c = chunk * CB + cg * 4;
-        const uint8_t* tile = smem + (sbase - dsmem_u32(smem)) + (size_t)b * BUF_BYTES;
-        float4 psum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < p.C) {
-            float4 acc[PX];
-            {
-                const float4 bz = *reinterpret_cast<const float4*>(p.bias + c);
-#pragma unroll
-                for (int q = 0; q < PX; ++q) acc[q] = bz;
-            }
-#pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                float4 in[SPAN];
-                const int iy = row * S + ky * D;
-#pragma unroll
-                for (int j = 0; j < SPAN; ++j) {
-                    bool used = false;
-#pragma unroll
-                    for (int kx = 0; kx < K; ++kx)
-#pragma unroll
-                        for (int q = 0; q < PX; ++q) used |= (q * S + kx * D == j);
-                    if (!used) continue;
-                    const int off = (iy * IW + xs * S + j) * ROW_BYTES;
-                    if (SPLIT_IN) {
-                        const uint2 a = *reinterpret_cast<const uint2*>(tile + off + cg * 8);
-                        const uint2 bb = *reinterpret_cast<const uint2*>(tile + PLANE_BYTES + off + cg * 8);
-                        const __half2* a2 = reinterpret_cast<const __half2*>(&a);
-                        const __half2* b2 = reinterpret_cast<const __half2*>(&bb);
-                        const float2 a01 = __half22float2(a2[0]), a23 = __half22float2(a2[1]);
-                        const float2 b01 = __half22float2(b2[0]), b23 = __half22float2(b2[1]);
-                        in[j] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
-                    } else {
-                        in[j] = *reinterpret_cast<const float4*>(tile + off + cg * 16);
-                    }
-                }
-#pragma unroll
-                for (int kx = 0; kx < K; ++kx) {
-                    const float4 w = *reinterpret_cast<const float4*>(tile + TILE_BYTES + ((ky * K + kx) * CB + cg * 4) * 4);
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < K) {
+                    w = *reinterpret_cast<const float4*>(p.w + (j * K + kx) * p.w_ld + c);
 #pragma unroll
                     for (int q = 0; q < PX; ++q) {
                         const float4 v = in[q * S + kx * D];
-                        acc[q].x = fmaf(v.x, w.x, acc[q].x);
-                        acc[q].y = fmaf(v.y, w.y, acc[q].y);
-                        acc[q].z = fmaf(v.z, w.z, acc[q].z);
-                        acc[q].w = fmaf(v.w, w.w, acc[q].w);
+                        acc[0][q].x = fmaf(v.x, w.x, acc[0][q].x);
+                        acc[0][q].y = fmaf(v.y, w.y, acc[0][q].y);
+                        acc[0][q].z = fmaf(v.z, w.z, acc[0][q].z);
+                        acc[0][q].w = fmaf(v.w, w.w, acc[0][q].w);
                     }
                 }
+                if (RY == 2 && j >= 1) {
+                    const float4 u = wprev[kx];          // weights of tap row j-1, loaded in the previous iteration
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) {
+                        const float4 v = in[q * S + kx * D];
+                        acc[RY - 1][q].x = fmaf(v.x, u.x, acc[RY - 1][q].x);
+                        acc[RY - 1][q].y = fmaf(v.y, u.y, acc[RY - 1][q].y);
+                        acc[RY - 1][q].z = fmaf(v.z, u.z, acc[RY - 1][q].z);
+                        acc[RY - 1][q].w = fmaf(v.w, u.w, acc[RY - 1][q].w);
+                    }
+                }
+                wprev[kx] = w;
             }
-            const int oy = oy0 + row;
+        }
+#pragma unroll
+        for (int ry = 0; ry < RY; ++ry) {
+            const int oy = oy0 + row0 + ry * D;
             if (oy < p.Ho) {
 #pragma unroll
                 for (int q = 0; q < PX; ++q) {
                     const int ox = ox0 + xs + q;
                     if (ox >= p.Wo) break;
-                    float4 a = acc[q];
+                    float4 a = acc[ry][q];
                     a.x = apply_act(a.x, p.act); a.y = apply_act(a.y, p.act);
                     a.z = apply_act(a.z, p.act); a.w = apply_act(a.w, p.act);
                     psum.x += a.x; psum.y += a.y; psum.z += a.z; psum.w += a.w;
@@ -312,11 +190,11 @@ dw_tma_persist_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_co
                 }
             }
         }
-        if (p.part) {
-            const int cw = chunk * CB + (tid % CG) * 4;
-            tile_channel_sums<CG>(psum, p.part + ((long long)n * tiles_img + sp) * p.part_ld + p.part_coff + cw, cw < p.C);
-        }
-        __syncthreads();          // every thread is done reading buffer b (and the reduction scratch) before the next iteration
+    }
+    if (p.part) {
+        const int cw = chunk * CB + (tid % CG) * 4;          // channel quad written by thread tid < CG
+        tile_channel_sums<CG>(psum, p.part + ((long long)n * gridDim.x + blockIdx.x) * p.part_ld + p.part_coff + cw,
+                              cw < p.C);
     }
 }
 
@@ -535,6 +413,17 @@ static EncodeTiledFn dw_get_encode() {
     return fn;
 }
 
+// Output rows per tile: 16 for the 5x5 stride-1 layers (two output rows per thread), else 8.  SKPS_DW_ROWS2=0 keeps 8
+// everywhere; plan.dw_tile_rows mirrors this (rows of the per-tile channel-sum buffer).
+int dw_tile_rows(int k, int s) {
+    static int rows2 = -1;
+    if (rows2 < 0) {
+        const char* e = getenv("SKPS_DW_ROWS2");
+        rows2 = (e && e[0] == '0') ? 0 : 1;
+    }
+    return (rows2 && k == 5 && s == 1) ? 2 * TH : TH;
+}
+
 static bool variant_ok(int k, int s, int d) {
     return (k == 3 && s == 1 && d == 1) || (k == 3 && s == 2 && d == 1) || (k == 5 && s == 1 && d == 1) ||
            (k == 5 && s == 2 && d == 1) || (k == 5 && s == 1 && d == 2);
@@ -555,7 +444,8 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
     SKPS_CHECK(dw_tma_supported(in, out, k, s, d, pad), "dw_tma: unsupported layer");
     const bool split = in.fmt == DT_SPLIT16;
     const int CB = split ? 64 : 32, esz = split ? 2 : 4;
-    const int IH = (TH - 1) * s + (k - 1) * d + 1, IW = (TW - 1) * s + (k - 1) * d + 1;
+    const int tht = dw_tile_rows(k, s);
+    const int IH = (tht - 1) * s + (k - 1) * d + 1, IW = (TW - 1) * s + (k - 1) * d + 1;
     for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)in.ld * esz, (cuuint64_t)in.W * in.ld * esz, (cuuint64_t)in.H * in.W * in.ld * esz};
@@ -574,7 +464,7 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
     kk.out = out.base; kk.out_fmt = out.fmt; kk.out_plane = out.plane; kk.out_ld = out.ld; kk.out_coff = out.c_off;
     kk.part = nullptr; kk.part_ld = 0; kk.part_coff = 0;
     if (part && part->base) {
-        const int tiles = ((out.H + TH - 1) / TH) * ((out.W + TW - 1) / TW);
+        const int tiles = ((out.H + tht - 1) / tht) * ((out.W + TW - 1) / TW);
         SKPS_CHECK(part->fmt == DT_F32 && part->c_stride == 1 && part->C == in.C && part->H * part->W == tiles &&
                    ((part->ld | part->c_off) & 3) == 0, "dw_tma: partial-sum view must be float32 [tiles=%d][C]", tiles);
         kk.part = (float*)part->base; kk.part_ld = part->ld; kk.part_coff = part->c_off;
@@ -585,45 +475,22 @@ int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float
     return 0;
 }
 
-static int dw_persist_mode() {
-    // SKPS_DW_PERSIST=1: persistent double-buffered variant.  Measured on B200 (student, batch 256) it is no faster than
-    // one tile per CTA (8.96 vs 8.96 ms per step; dilated 5x5 layer 236 vs 224 us): these kernels are bound by
-    // shared-memory bandwidth (85 LDS.128 per 400 FMAs), not by the tile load latency, and the second buffer halves
-    // the resident CTAs.  Default: one tile per CTA.
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("SKPS_DW_PERSIST");
-        mode = (e && e[0] == '1') ? 1 : 0;
+template <int K, int S, int D, bool SPLIT, int RY>
+static int launch_variant_r(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKPS_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, D, SPLIT, RY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
     }
-    return mode;
+    dw_tma_kernel<K, S, D, SPLIT, RY><<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.hi, L.lo, k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
 }
 
 template <int K, int S, int D, bool SPLIT>
 static int launch_variant(const DwTmaLayer& L, const DwTmaK& k, dim3 grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    static int ctas_per_sm = 1, sms = 148;
-    const int buf_bytes = L.smem_bytes - 128 + K * K * (SPLIT ? 64 : 32) * 4;      // tile + this chunk's weights
-    const int persist_smem = 2 * buf_bytes + 128;
-    if (!attr_set) {
-        SKPS_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SKPS_CUDA(cudaFuncSetAttribute(dw_tma_persist_kernel<K, S, D, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       220 * 1024));
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        SKPS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, dw_tma_persist_kernel<K, S, D, SPLIT>,
-                                                                DW_THREADS, persist_smem));
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-        attr_set = true;
-    }
-    const long long total = (long long)grid.x * grid.y * grid.z;
-    if (dw_persist_mode() && total > (long long)sms * ctas_per_sm && persist_smem <= 220 * 1024) {
-        dw_tma_persist_kernel<K, S, D, SPLIT><<<sms * ctas_per_sm, DW_THREADS, persist_smem, stream>>>(L.hi, L.lo, k);
-    } else {
-        dw_tma_kernel<K, S, D, SPLIT><<<grid, DW_THREADS, L.smem_bytes, stream>>>(L.hi, L.lo, k);
-    }
-    SKPS_CUDA(cudaGetLastError());
-    return 0;
+    if (K == 5 && S == 1 && dw_tile_rows(K, S) == 2 * TH) return launch_variant_r<K, S, D, SPLIT, (K == 5 && S == 1) ? 2 : 1>(L, k, grid, stream);
+    return launch_variant_r<K, S, D, SPLIT, 1>(L, k, grid, stream);
 }
 
 int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream) {
@@ -631,7 +498,8 @@ int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream)
     k.img0 = img0;
     k.chunks = L.chunks;
     k.batch = batch;
-    dim3 grid(((k.Ho + TH - 1) / TH) * ((k.Wo + TW - 1) / TW), L.chunks, batch);
+    const int tht = dw_tile_rows(L.k_size, L.stride);
+    dim3 grid(((k.Ho + tht - 1) / tht) * ((k.Wo + TW - 1) / TW), L.chunks, batch);
 #define DW_CASE(K_, S_, D_)                                                                              \
     if (L.k_size == K_ && L.stride == S_ && L.dil == D_)                                                 \
         return L.split ? launch_variant<K_, S_, D_, true>(L, k, grid, stream)                            \

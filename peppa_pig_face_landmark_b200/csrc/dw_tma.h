@@ -26,7 +26,7 @@ struct DwTmaLayer {
 bool dw_tma_supported(const TView& in, const TView& out, int k, int s, int d, int pad);
 int dw_tma_prepare(DwTmaLayer& L, const TView& in, const TView& out, const float* w, const float* bias, int k, int s,
                    int d, int pad, int act, int max_batch, const TView* part = nullptr);
-constexpr int DW_TILE_H = 8, DW_TILE_W = 16;     // output tile of the TMA depthwise kernels (partial-sum rows per image)
+int dw_tile_rows(int k, int s);                  // output rows per tile (8, or 16 for 5x5 stride-1 layers); tiles are 16 columns wide
 int dw_tma_launch(const DwTmaLayer& L, int batch, int img0, cudaStream_t stream);
 
 // depthwise3x3(concat(bilinear_x2(low), skip)): TMA-staged low-res tiles for the up-sampled channels plus a

@@ -1029,19 +1029,37 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
             int idx = si[j][c];
             if (idx != 0x7fffffff && (v > best || (v == best && idx < bi))) { best = v; bi = idx; }
         }
-        float ox, oy;
-        if (off.feat) {
-            const long long fe = ((long long)n * HW + bi) * off.ld + off.coff;
+        si[0][c] = bi;
+    }
+    if (off.feat) {
+        // split head: every position group takes one eighth of the K-long dot products at the arg-max pixel; the eight
+        // partial sums are added in group order
+        __syncthreads();
+        float px = 0.f, py = 0.f;
+        if (c < P) {
+            const int am = si[0][c];
+            const int kper = ((off.K + 31) / 32) * 4, k0 = g * kper, k1 = min(off.K, k0 + kper);
+            const long long fe = ((long long)n * HW + am) * off.ld + off.coff;
             const float* wx = off.w + (long long)c * off.K;
             const float* wy = off.w + (long long)(P + c) * off.K;
-            ox = off.b[c]; oy = off.b[P + c];
-            for (int k = 0; k < off.K; k += 4) {
+            for (int k = k0; k < k1; k += 4) {
                 const float4 a = ld4(off.feat, off.fmt, off.plane, fe + k);
                 const float4 u = __ldg(reinterpret_cast<const float4*>(wx + k));
                 const float4 v = __ldg(reinterpret_cast<const float4*>(wy + k));
-                ox = fmaf(a.x, u.x, ox); ox = fmaf(a.y, u.y, ox); ox = fmaf(a.z, u.z, ox); ox = fmaf(a.w, u.w, ox);
-                oy = fmaf(a.x, v.x, oy); oy = fmaf(a.y, v.y, oy); oy = fmaf(a.z, v.z, oy); oy = fmaf(a.w, v.w, oy);
+                px = fmaf(a.x, u.x, px); px = fmaf(a.y, u.y, px); px = fmaf(a.z, u.z, px); px = fmaf(a.w, u.w, px);
+                py = fmaf(a.x, v.x, py); py = fmaf(a.y, v.y, py); py = fmaf(a.z, v.z, py); py = fmaf(a.w, v.w, py);
             }
+        }
+        __syncthreads();                 // all groups have read the arg-max before sv/si are reused
+        sv[g][c] = px;
+        reinterpret_cast<float*>(si)[g * 128 + c] = py;
+        __syncthreads();
+    }
+    if (g == 0 && c < P) {
+        float ox, oy;
+        if (off.feat) {
+            ox = off.b[c]; oy = off.b[P + c];
+            for (int j = 0; j < 8; ++j) { ox += sv[j][c]; oy += reinterpret_cast<float*>(si)[j * 128 + c]; }
         } else {
             ox = base[(long long)bi * ld + P + c];
             oy = base[(long long)bi * ld + 2 * P + c];

@@ -536,7 +536,7 @@ class _Lowerer:
             return False
         if xin.C != out_v.C or xin.C not in (24, 40) or xin.buf.dtype == P.DT_U8:
             return False
-        if xin.c_stride != 1 or out_v.c_stride != 1 or (xin.buf.C | xin.c_off) % 8 or (out_v.buf.C | out_v.c_off) % 2:
+        if xin.c_stride != 1 or out_v.c_stride != 1 or (xin.buf.C | xin.c_off) % 8 or (out_v.buf.C | out_v.c_off) % 8:
             return False
         return xin.H >= 8 and xin.W >= 16
 
@@ -873,7 +873,7 @@ def _fuse_se_chain(pl):
         if fc2.outs[0].C != C or fc1.ins[0].C != C or (C + Cr) * 8 * 4 > 96 * 1024 or C % 4:
             continue
         o = dw.outs[0]
-        tiles = -(-o.H // P.DW_TILE_H) * -(-o.W // P.DW_TILE_W)
+        tiles = -(-o.H // P.dw_tile_rows(dw.k[0], dw.s[0])) * -(-o.W // P.DW_TILE_W)
         pb = pl.new_buf(C, tiles, 1, P.DT_F32, dw.name + ":tile_sums")
         pv = P.View(pb, 0, 1, C)
         dw.outs = [dw.outs[0], pv]

@@ -100,7 +100,13 @@ FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo ma
 FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
 FLAG_MMA = 16         # 3x3 conv with few channels on the halo-tile mma.sync kernel (csrc/conv_mma.cu): w = packed fp16 hi/lo
 FLAG_GAP_PARTIAL = 8  # depthwise conv also writes per-tile channel sums of its output to outs[1] ([tiles][C] per sample)
-DW_TILE_H, DW_TILE_W = 8, 16     # output tile of csrc/dw_tma.cu (rows of the partial-sum buffer per sample)
+DW_TILE_W = 16
+
+
+def dw_tile_rows(k, s):
+    """Output rows per tile of csrc/dw_tma.cu (rows of the per-tile channel-sum buffer): 16 for 5x5 stride-1 layers, else 8."""
+    import os
+    return 16 if (k == 5 and s == 1 and os.environ.get("SKPS_DW_ROWS2", "1") != "0") else 8
 
 
 class Plan:

@@ -15,7 +15,7 @@ echo "== bench (default)" | tee -a $OUT/steps.log
 timeout 600 python bench.py --steps 30 --warmup 5 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/steps.log
 python -c "
 import json; d=json.load(open('$OUT/bench.json')); print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'roof', d['roofline']['achieved'], d['roofline']['kernel_ms'])"
-for sw in ${AB_SWITCHES:-"SKPS_DW_PERSIST=1" "SKPS_HM_SPLIT=0" "SKPS_SE_FUSE=0"}; do
+for sw in ${AB_SWITCHES:-"SKPS_DW_ROWS2=0" "SKPS_SE_FUSE=0"}; do
   env $sw timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_$sw.json 2> $OUT/bench_$sw.err
   python -c "
 import json; d=json.load(open('$OUT/bench_$sw.json')); print('$sw', 'value', d['value'], 'ms', d['ms_per_step'])" | tee -a $OUT/steps.log

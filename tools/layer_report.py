@@ -30,7 +30,10 @@ def report(which="student", batch=2, out=sys.stdout):
     sess = Session(path)
     worst = 0.0
     rows = []
-    written = {v.buf.idx for op in eng.plan.ops for v in op.outs}      # fusions leave some named tensors unmaterialised
+    written = {}                                      # buffer -> logical channels some op writes (fusions leave tensors unmaterialised)
+    for op in eng.plan.ops:
+        for v in op.outs:
+            written[v.buf.idx] = max(written.get(v.buf.idx, 0), v.c_off + (v.C - 1) * v.c_stride + 1)
     for n in range(batch):
         xf = x_u8[n].transpose(2, 0, 1).astype(np.float32)[None] / np.float32(255.)
         ref_outs, kept = sess.run(xf, keep="all")
@@ -42,7 +45,7 @@ def report(which="student", batch=2, out=sys.stdout):
                 continue
             got = eng.read_buffer(b.idx, batch)[n]
             ref = ref[0].transpose(1, 2, 0)
-            nc = min(ref.shape[-1], b.C)            # buffers may be channel-padded; the split heat-map head keeps only the score maps
+            nc = min(ref.shape[-1], written[b.idx])  # buffers may be channel-padded; the split heat-map head keeps only the score maps
             got, ref = got[..., :nc], ref[..., :nc]
             if got.shape != ref.shape:
                 rows.append((b.idx, b.name, "SHAPE %s vs %s" % (got.shape, ref.shape)))
