@@ -56,8 +56,8 @@ def test_teacher_plan_matches_oracle_graph(teacher_onnx):
     # (Cout 24 on >= 32x32 maps: pw_small_kernel) rides the tcgen05 kernel
     thin = [o for o in convs if not (o.flags & P.FLAG_TC) and list(o.k) == [1, 1] and o.outs[0].C == 16
             and o.ins[0].C <= 32 and o.outs[0].H * o.outs[0].W >= 1024]
-    mma = [o for o in convs if o.flags & P.FLAG_MMA]         # 24->24 @64x64 and 40->40 @32x32 branch convs (halo-tile kernel)
-    assert len(mma) == 128 and all(list(o.k) == [3, 3] and o.ins[0].C in (24, 40) for o in mma)
+    mma = [o for o in convs if o.flags & P.FLAG_MMA]         # 24->24 @64x64 branch convs (halo-tile mma.sync kernel)
+    assert len(mma) == 64 and all(list(o.k) == [3, 3] and o.ins[0].C == 24 for o in mma)
     assert len(convs) - len(tc) - len(mma) - len(thin) == 4 and sum(o.type == P.OP_ADDN for o in plan.ops) == 40
     assert not any(o.type == P.OP_RESIZE_NEAREST and o.ins[0].H > 1 for o in plan.ops)   # HRNet upsamples are fused
     crops = T.synthetic_crops(2, 256, 99)

@@ -31,9 +31,16 @@ def report(which="student", batch=2, out=sys.stdout):
     worst = 0.0
     rows = []
     written = {}                                      # buffer -> logical channels some op writes (fusions leave tensors unmaterialised)
+    read = {}
     for op in eng.plan.ops:
         for v in op.outs:
             written[v.buf.idx] = max(written.get(v.buf.idx, 0), v.c_off + (v.C - 1) * v.c_stride + 1)
+        for v in op.ins:
+            if v is not None:
+                read[v.buf.idx] = max(read.get(v.buf.idx, 0), v.c_off + (v.C - 1) * v.c_stride + 1)
+    for k in written:                                 # a conv may also write the zero padding channels of its buffer
+        if k in read:
+            written[k] = min(written[k], read[k])
     for n in range(batch):
         xf = x_u8[n].transpose(2, 0, 1).astype(np.float32)[None] / np.float32(255.)
         ref_outs, kept = sess.run(xf, keep="all")
