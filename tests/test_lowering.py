@@ -86,3 +86,103 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def test_onnx_writer_round_trips_the_shipped_graphs(tmp_path):
+    """onnx_writer.save_onnx is the inverse of onnx_loader.load_onnx on everything the shipped files contain
+    (0-d tensors, int64 constants, string/int/float/list attributes)."""
+    from peppa_pig_face_landmark_b200.onnx_loader import load_onnx
+    from peppa_pig_face_landmark_b200.onnx_writer import save_onnx
+    from oracle import onnx_lite
+    for f in ("kps_student.onnx", "yolov5n-0.5.onnx"):
+        g = load_onnx(os.path.join(PRE, f))
+        out = str(tmp_path / f)
+        save_onnx(out, g.nodes, g.weights, [(g.inputs[0], g.input_shapes[g.inputs[0]])], [(o, [1]) for o in g.outputs])
+        g2, g3 = load_onnx(out), onnx_lite.load(out)           # product reader and the oracle's independent reader
+        assert len(g.nodes) == len(g2.nodes) == len(g3.nodes) and g2.inputs == g.inputs and g2.outputs == g.outputs
+        for a, b, c in zip(g.nodes, g2.nodes, g3.nodes):
+            assert (a.op, a.name, a.inputs, a.outputs) == (b.op, b.name, b.inputs, b.outputs) == (c.op, c.name, c.inputs, c.outputs)
+            assert a.attrs.keys() == b.attrs.keys()
+            for k, va in a.attrs.items():
+                if isinstance(va, np.ndarray):
+                    assert va.dtype == b.attrs[k].dtype and va.shape == b.attrs[k].shape and np.array_equal(va, b.attrs[k])
+                    assert np.array_equal(va, c.attrs[k])
+                else:
+                    assert va == b.attrs[k] == c.attrs[k]
+        assert all(np.array_equal(v, g2.weights[k]) and v.dtype == g2.weights[k].dtype for k, v in g.weights.items())
+
+
+def test_student_plan_fusions():
+    """The fusions the student plan relies on: 8 squeeze-excite chains (GAP + 2 FC -> per-tile sums + one gate op),
+    both decoder heads (upsample + concat + depthwise), the split heat-map head."""
+    from peppa_pig_face_landmark_b200 import lowering, plan as P
+    plan = lowering.lower(os.path.join(PRE, "kps_student.onnx"), (256, 256))
+    kinds = [o.type for o in plan.ops]
+    assert kinds.count(P.OP_SE_FC) == 8 and kinds.count(P.OP_UPCAT_DW) == 2 and kinds.count(P.OP_GAP) == 2
+    for se in (o for o in plan.ops if o.type == P.OP_SE_FC):
+        dw = [o for o in plan.ops if o.type == P.OP_DWCONV and len(o.outs) == 2 and o.outs[1].buf is se.ins[0].buf]
+        assert len(dw) == 1 and dw[0].flags & P.FLAG_GAP_PARTIAL
+        o = dw[0].outs[0]
+        th = P.dw_tile_rows(dw[0].k[0], dw[0].s[0])
+        assert se.ins[0].buf.H == -(-o.H // th) * -(-o.W // P.DW_TILE_W) and se.ints[3] == o.H * o.W
+    dec = plan.ops[-1]
+    hm = plan.ops[-2]
+    assert dec.type == P.OP_HM_DECODE and len(dec.ins) == 2 and dec.w.shape == (196, 128) and dec.ints[:2] == [98, 128]
+    assert hm.type == P.OP_CONV and hm.outs[0].buf.C == 104 and hm.ins[0].buf is dec.ins[1].buf
+
+
+def test_upcat_effective_weights_equal_upsample_then_depthwise():
+    """plan.upcat_effective_weights: depthwise3x3(bilinear_x2(low)) as a class-dependent 3x3 stencil on the low-res map."""
+    import torch
+    import torch.nn.functional as F
+    from peppa_pig_face_landmark_b200 import plan as P
+    rng = np.random.default_rng(0)
+    C, Hl, Wl = 8, 5, 7
+    low = rng.standard_normal((1, C, Hl, Wl)).astype(np.float32)
+    w = rng.standard_normal((9, C)).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    up = F.interpolate(torch.from_numpy(low), scale_factor=2, mode="bilinear", align_corners=False)
+    ref = F.conv2d(up, torch.from_numpy(w.T.reshape(C, 1, 3, 3).copy()), torch.from_numpy(b), padding=1, groups=C).numpy()[0]
+    we = P.upcat_effective_weights(w)
+    H, W = 2 * Hl, 2 * Wl
+
+    def cls(p, n):
+        return 0 if p == 0 else (3 if p == n - 1 else 1 + (p & 1))
+    out = np.zeros((C, H, W), np.float32)
+    for y in range(H):
+        for x in range(W):
+            acc = b.astype(np.float64).copy()
+            for a in range(3):
+                for bb in range(3):
+                    acc += we[cls(y, H), cls(x, W), a, bb].astype(np.float64) * \
+                        low[0, :, min(max(y // 2 + a - 1, 0), Hl - 1), min(max(x // 2 + bb - 1, 0), Wl - 1)]
+            out[:, y, x] = acc
+    assert np.abs(out - ref).max() < 5e-6
+
+
+def test_pad_channels_on_a_synthetic_residual_graph(tmp_path):
+    """18-channel tensors between dense convs are zero-padded to 24 without changing the result; tensors that reach a
+    depthwise conv or a graph output are left alone."""
+    import torch
+    from peppa_pig_face_landmark_b200 import lowering
+    from peppa_pig_face_landmark_b200.onnx_loader import OnnxNode, load_onnx
+    from peppa_pig_face_landmark_b200.onnx_writer import save_onnx
+    from oracle.onnx_exec import Session
+    rng = np.random.default_rng(1)
+    conv = dict(dilations=[1, 1], group=1, kernel_shape=[3, 3], pads=[1, 1, 1, 1], strides=[1, 1])
+    W = {"w0": rng.standard_normal((18, 3, 3, 3)).astype(np.float32) * 0.2, "b0": rng.standard_normal(18).astype(np.float32),
+         "w1": rng.standard_normal((18, 18, 3, 3)).astype(np.float32) * 0.1,
+         "w2": rng.standard_normal((16, 18, 3, 3)).astype(np.float32) * 0.1}
+    nodes = [OnnxNode("Conv", "c0", ["input", "w0", "b0"], ["t0"], dict(conv)), OnnxNode("Relu", "r0", ["t0"], ["t1"], {}),
+             OnnxNode("Conv", "c1", ["t1", "w1"], ["t2"], dict(conv)), OnnxNode("Add", "a", ["t2", "t1"], ["t3"], {}),
+             OnnxNode("Relu", "r1", ["t3"], ["t4"], {}), OnnxNode("Conv", "c2", ["t4", "w2"], ["out"], dict(conv))]
+    path = str(tmp_path / "res.onnx")
+    save_onnx(path, nodes, W, [("input", [1, 3, 16, 16])], [("out", [1, 16, 16, 16])])
+    g = lowering.pad_channels(load_onnx(path))
+    assert g.weights["w0"].shape == (24, 3, 3, 3) and g.weights["b0"].shape == (24,)
+    assert g.weights["w1"].shape == (24, 24, 3, 3) and g.weights["w2"].shape == (16, 24, 3, 3)
+    padded = str(tmp_path / "res_padded.onnx")
+    save_onnx(padded, [OnnxNode(n.op, n.name, n.inputs, n.outputs, {k: v for k, v in n.attrs.items() if not k.startswith("_")})
+                       for n in g.nodes], g.weights, [("input", [1, 3, 16, 16])], [("out", [1, 16, 16, 16])])
+    x = rng.standard_normal((1, 3, 16, 16)).astype(np.float32)
+    assert np.abs(Session(path).run(x)[0] - Session(padded).run(x)[0]).max() < 1e-5
