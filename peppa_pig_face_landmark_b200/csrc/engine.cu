@@ -404,7 +404,12 @@ extern "C" SKPS_API int skps_engine_launches_per_forward(const skps_engine* e) {
 extern "C" SKPS_API int skps_engine_launches_for_batch(const skps_engine* e, int batch) {
     if (!e) return 0;
     long long n = 0;
-    for (const auto& sg : e->segments) n += (long long)(sg.end - sg.first) * ((batch + sg.chunk - 1) / sg.chunk);
+    for (const auto& sg : e->segments) {
+        long long per_sweep = 0;
+        for (int i = sg.first; i < sg.end; ++i)      // the TMA fused-upsample op is two kernels (up-sampled part + skip part)
+            per_sweep += (e->ops[i].type == OP_UPCAT_DW && e->upt[i].valid) ? 2 : 1;
+        n += per_sweep * ((batch + sg.chunk - 1) / sg.chunk);
+    }
     return (int)n;
 }
 
