@@ -9,7 +9,7 @@ namespace skps {
 
 struct DwTmaK {
     int C, Ho, Wo, pad, act, img0;
-    int chunks, batch;           // persistent kernel: channel chunks per image, images in this launch
+    int chunks, batch;           // channel chunks per image, images in this launch (grid = tiles x chunks x batch)
     float* part; int part_ld, part_coff;   // optional [n][tile][C] per-tile channel sums of the outputs (squeeze-excite GAP)
     int w_ld;                    // channel stride of the weight rows (>= C when this layer is a channel slice)
     const float* w; const float* bias;
