@@ -159,8 +159,7 @@ class Plan:
             op.b_off = put(op.b) if op.b is not None else -1
             if op.extra is not None:
                 op.ints = [put(op.extra)] + list(op.ints[1:])
-        # tail padding: the depthwise kernels prefetch whole 64-channel weight rows (csrc/dw_tma.cu), which may run a few
-        # floats past a row whose channel count is not a multiple of 64
+        # tail slack: kernels that read weight rows in whole 16-byte / 64-channel pieces never run past the allocation
         parts.append(np.zeros(256, np.float32))
         return np.concatenate(parts)
 
