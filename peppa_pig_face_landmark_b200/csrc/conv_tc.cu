@@ -17,6 +17,7 @@
 //   SM, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "../../include/skps_b200.h"
 #include "common.h"
@@ -471,13 +472,29 @@ static const float* zero_bias() {
     return z;
 }
 
+// Tile width for an Ho x Wo OUTPUT map (0 = no tiling): 128-pixel tiles are bw x (128/bw) blocks of one image.
+// Default rule: bw = min(W, 128) (W | 128 or 128 | W).  SKPS_TC_ANY_W=1 (experimental, not yet validated on hardware for the
+// new shapes) also accepts any W that some bw in {64,32,16,8} divides, e.g. 16 x 8 tiles on 48- or 80-wide maps; for the
+// shapes the default rule accepts it picks the same bw.
+static int tc_pick_bw(int H, int W) {
+    static int any_w = -1;
+    if (any_w < 0) {
+        const char* e = getenv("SKPS_TC_ANY_W");
+        any_w = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (W >= TC_BM && W % TC_BM == 0) return TC_BM;
+    if (W < TC_BM && TC_BM % W == 0 && H % (TC_BM / W) == 0) return W;
+    if (any_w)
+        for (int bw = 64; bw >= 8; bw >>= 1)
+            if (W % bw == 0 && H % (TC_BM / bw) == 0) return bw;
+    return 0;
+}
+
 // Ho x Wo = OUTPUT map: 128-pixel tiles must be whole row blocks of one image, or whole images (Ho*Wo | 128)
 bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff) {
     if (W < 8 || (Cin % 8) || (in_ld % 8) || (in_coff % 8)) return false;
-    if (W >= TC_BM) return W % TC_BM == 0;
-    if (TC_BM % W) return false;
-    if (H * W < TC_BM) return TC_BM % (H * W) == 0;
-    return H % (TC_BM / W) == 0;
+    if (H * W < TC_BM) return TC_BM % W == 0 && TC_BM % (H * W) == 0;
+    return tc_pick_bw(H, W) != 0;
 }
 
 int tc_prepare(TcLayer& L, const TcSetup& s) {
@@ -493,9 +510,9 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     L.k = TcK();
     TcK& k = L.k;
     k.H = Ho; k.W = Wo; k.stride = stride;             // the kernel's H, W are the OUTPUT map
-    k.bw = Wo >= TC_BM ? TC_BM : Wo;
-    k.bh = TC_BM / k.bw;
     k.ipt = Ho * Wo < TC_BM ? TC_BM / (Ho * Wo) : 1;
+    k.bw = k.ipt > 1 ? Wo : tc_pick_bw(Ho, Wo);
+    k.bh = TC_BM / k.bw;
     k.tiles_per_img = k.ipt > 1 ? 1 : (Ho / k.bh) * (Wo / k.bw);
     k.taps = s.kh * s.kw; k.kw = s.kw; k.dil = s.dil; k.pad = s.pad;
     k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;

@@ -559,13 +559,14 @@ class _Lowerer:
         if xin.H % s[0] or xin.W % s[0]:
             return False
         H, W = xin.H // s[0], xin.W // s[0]              # output map: 128-pixel tiles = row blocks, or whole images
-        if W >= 128:
-            return W % 128 == 0
-        if W < 8 or 128 % W:
+        if W < 8:
             return False
         if H * W < 128:                                  # several whole images per tile (SKPS_TC_SMALL=0: CUDA-core kernel)
-            return 128 % (H * W) == 0 and os.environ.get("SKPS_TC_SMALL", "1") != "0"
-        return H % (128 // W) == 0
+            return 128 % W == 0 and 128 % (H * W) == 0 and os.environ.get("SKPS_TC_SMALL", "1") != "0"
+        if (W % 128 == 0) if W >= 128 else (128 % W == 0 and H % (128 // W) == 0):
+            return True
+        # SKPS_TC_ANY_W=1 (experimental, mirrors csrc/conv_tc.cu tc_pick_bw): bw x 128/bw tiles for any W some bw divides
+        return os.environ.get("SKPS_TC_ANY_W", "0") == "1" and any(W % bw == 0 and H % (128 // bw) == 0 for bw in (64, 32, 16, 8))
 
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
