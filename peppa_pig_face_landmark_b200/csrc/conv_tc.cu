@@ -209,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int tiles_x = p.W / p.bw;
+            const int tiles_x = (p.W + p.bw - 1) / p.bw;       // ragged maps: edge tiles hang over, TMA zero-fills / clips
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
                 int img[2], y0[2], x0[2];
@@ -291,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         int store_i = 0;                 // TMA stores issued by this warp group so far
-        const int tiles_x = p.W / p.bw;
+        const int tiles_x = (p.W + p.bw - 1) / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
             mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
@@ -304,7 +304,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // multi-image tiles (ipt > 1): bw = W, bh = ipt*H, so y runs past H into the next image and the linear
             // pixel index below is still right; rows of images past the batch are computed but never stored
             const int y = (t / tiles_x) * p.bh + row / p.bw, x = (t % tiles_x) * p.bw + row % p.bw;
-            const bool row_ok = p.ipt == 1 || img + y / p.H < p.img_end;
+            // rows of an edge tile that hang over the map (ragged tiling) are computed but never stored
+            const bool row_ok = p.ipt == 1 ? (y < p.H && x < p.W) : img + y / p.H < p.img_end;
             const long long pix = row_ok ? ((long long)img * p.H + y) * p.W + x : 0;
             const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + (uint32_t)u * 128u + ((uint32_t)(q * 32) << 16);
             const int co_tile = n_idx * p.n_tile;
@@ -473,24 +474,31 @@ static const float* zero_bias() {
 }
 
 // Tile width for an Ho x Wo OUTPUT map (0 = no tiling): 128-pixel tiles are bw x (128/bw) blocks of one image.
-// Default rule: bw = min(W, 128) (W | 128 or 128 | W).  SKPS_TC_ANY_W=1 (experimental, not yet validated on hardware for the
-// new shapes) also accepts any W that some bw in {64,32,16,8} divides, e.g. 16 x 8 tiles on 48- or 80-wide maps; for the
-// shapes the default rule accepts it picks the same bw.
+// Maps whose width divides (or is a multiple of) 128 use row-block tiles (bw = min(W, 128)) that cover the map exactly.
+// Any other map (the detector's 48x80 / 24x40 / 12x20, re-targeted @192/@320 exports) gets the bw in {64,32,16,8} with the
+// fewest tiles, edge tiles hanging over the right/bottom border: the TMA loads zero-fill and the TMA stores clip what
+// lies outside, the direct-store path masks it.  SKPS_TC_ANY_W=0 restores the exact-cover-only rule.
 static int tc_pick_bw(int H, int W) {
     static int any_w = -1;
     if (any_w < 0) {
         const char* e = getenv("SKPS_TC_ANY_W");
-        any_w = (e && e[0] == '1') ? 1 : 0;
+        any_w = (e && e[0] == '0') ? 0 : 1;
     }
     if (W >= TC_BM && W % TC_BM == 0) return TC_BM;
     if (W < TC_BM && TC_BM % W == 0 && H % (TC_BM / W) == 0) return W;
-    if (any_w)
-        for (int bw = 64; bw >= 8; bw >>= 1)
-            if (W % bw == 0 && H % (TC_BM / bw) == 0) return bw;
-    return 0;
+    if (!any_w) return 0;
+    int best = 0, best_tiles = 1 << 30;
+    for (int bw = 64; bw >= 8; bw >>= 1) {
+        const int bh = TC_BM / bw;
+        if (bw > W + 7 || bh > H + 7) continue;                  // keep boxes within ~the map
+        const int tiles = ((W + bw - 1) / bw) * ((H + bh - 1) / bh);
+        if (tiles < best_tiles) { best_tiles = tiles; best = bw; }
+    }
+    return best;
 }
 
-// Ho x Wo = OUTPUT map: 128-pixel tiles must be whole row blocks of one image, or whole images (Ho*Wo | 128)
+// Ho x Wo = OUTPUT map: 128-pixel tiles are row blocks of one image (ragged at the border if need be), or whole images
+// (Ho*Wo | 128)
 bool tc_shape_ok(int H, int W, int Cin, int in_ld, int in_coff) {
     if (W < 8 || (Cin % 8) || (in_ld % 8) || (in_coff % 8)) return false;
     if (H * W < TC_BM) return TC_BM % W == 0 && TC_BM % (H * W) == 0;
@@ -513,7 +521,7 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.ipt = Ho * Wo < TC_BM ? TC_BM / (Ho * Wo) : 1;
     k.bw = k.ipt > 1 ? Wo : tc_pick_bw(Ho, Wo);
     k.bh = TC_BM / k.bw;
-    k.tiles_per_img = k.ipt > 1 ? 1 : (Ho / k.bh) * (Wo / k.bw);
+    k.tiles_per_img = k.ipt > 1 ? 1 : ((Ho + k.bh - 1) / k.bh) * ((Wo + k.bw - 1) / k.bw);
     k.taps = s.kh * s.kw; k.kw = s.kw; k.dil = s.dil; k.pad = s.pad;
     k.cchunks = (s.Cin + TC_BK - 1) / TC_BK;
     k.Cout = s.Cout; k.act = s.act; k.out_scale = s.out_scale;

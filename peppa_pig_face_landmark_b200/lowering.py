@@ -565,8 +565,8 @@ class _Lowerer:
             return 128 % W == 0 and 128 % (H * W) == 0 and os.environ.get("SKPS_TC_SMALL", "1") != "0"
         if (W % 128 == 0) if W >= 128 else (128 % W == 0 and H % (128 // W) == 0):
             return True
-        # SKPS_TC_ANY_W=1 (experimental, mirrors csrc/conv_tc.cu tc_pick_bw): bw x 128/bw tiles for any W some bw divides
-        return os.environ.get("SKPS_TC_ANY_W", "0") == "1" and any(W % bw == 0 and H % (128 // bw) == 0 for bw in (64, 32, 16, 8))
+        # any other map: ragged bw x 128/bw tiles (mirrors csrc/conv_tc.cu tc_pick_bw); SKPS_TC_ANY_W=0 turns them off
+        return os.environ.get("SKPS_TC_ANY_W", "1") != "0" and any(bw <= W + 7 and 128 // bw <= H + 7 for bw in (64, 32, 16, 8))
 
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
