@@ -110,6 +110,15 @@ SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, c
                                  float out_scale, const float* residual, int out_split, float* out, int stride,
                                  int res_first, int max_batch);
 
+/* Debug/unit-test entry of the fused producer -> 1x1 conv kernels (csrc/conv_xf.cu): mode 0 = squeeze-excite scale
+ * (x * gate[n,c]) ahead of the conv, mode 1 = depthwise 3x3 [over concat(bilinear_x2(low), x)] ahead of the conv.
+ * Replaces, for one layer, what onnxruntime runs for the reference's ONNX nodes Mul->Conv / Resize->Concat->Conv(dw)->Conv
+ * (Skps/core/api/onnx_model_base.py:23).  Host float32 NHWC in/out; w_hi/w_lo as packed by plan.pack_tc_weights. */
+SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int H, int W, int Cx, int x_split, const float* low, int Cl,
+                                const float* gate, const float* dww, int dw_act, const void* w_hi, const void* w_lo,
+                                const float* bias, int Cout, int act, int n_tile, float out_scale, const float* residual,
+                                int res_first, int out_split, float* out);
+
 /* Unit-test entry for the few-channel 3x3 convolution kernel (csrc/conv_mma.cu; Cin == Cout == C in {24, 40}, the
  * Teacher's HRNet branch convs): x, residual, out float32 NHWC; w_packed float16 [tap][hi/lo][C][C] as packed by
  * plan.pack_mma_weights. */

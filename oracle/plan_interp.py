@@ -92,6 +92,23 @@ class PlanInterp:
                 w = torch.from_numpy(op.w).T.reshape(C, 1, 3, 3).contiguous()
                 y = F.conv2d(x, w, torch.from_numpy(op.b), padding=1, groups=C)
                 wr(op.outs[0], _act(y, op.act).permute(0, 2, 3, 1))
+            elif t == P.OP_DWPW:
+                x = rd(op.ins[0]).permute(0, 3, 1, 2)
+                if op.ins[2] is not None:
+                    low = rd(op.ins[2]).permute(0, 3, 1, 2)
+                    x = torch.cat([F.interpolate(low, scale_factor=2, mode="bilinear", align_corners=False), x], 1)
+                C = x.shape[1]
+                wd = torch.from_numpy(op.dw_w).T.reshape(C, 1, 3, 3).contiguous()
+                y = _act(F.conv2d(x, wd, torch.from_numpy(op.dw_b), padding=1, groups=C), op.dw_act)
+                w = torch.from_numpy(op.w_ref).permute(0, 3, 1, 2).contiguous()
+                y = F.conv2d(y, w, torch.from_numpy(op.b) if op.b is not None else None).permute(0, 2, 3, 1)
+                if op.ins[1] is not None and (op.flags & P.FLAG_RES_FIRST):
+                    y = _act(y + rd(op.ins[1]), op.act)
+                else:
+                    y = _act(y, op.act)
+                    if op.ins[1] is not None:
+                        y = y + rd(op.ins[1])
+                wr(op.outs[0], y)
             elif t == P.OP_MAXPOOL2:
                 x = rd(op.ins[0]).permute(0, 3, 1, 2)
                 wr(op.outs[0], F.max_pool2d(x, 2, 2, 0, ceil_mode=True).permute(0, 2, 3, 1))

@@ -16,6 +16,7 @@ SOURCES = {
     "pipeline.cu": [],
     "conv_simt.cu": [],
     "conv_tc.cu": [],
+    "conv_xf.cu": [],
     "conv_mma.cu": [],
     "dw_tma.cu": [],
     "ops_misc.cu": [],

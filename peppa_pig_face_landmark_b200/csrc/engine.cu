@@ -14,6 +14,7 @@
 #include "common.h"
 #include "conv_mma.h"
 #include "conv_tc.h"
+#include "conv_xf.h"
 #include "dw_tma.h"
 
 namespace skps {
@@ -50,6 +51,7 @@ struct skps_engine {
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
     std::vector<ConvMmaLayer> mma;        // per op; valid where ops[i].flags & FLAG_MMA
+    std::vector<XfLayer> xf;              // per op; fused producer -> pointwise conv layers (OP_DWPW, OP_CONV with FLAG_XF)
     std::vector<DwTmaLayer> dwt;          // per op; TMA-staged depthwise layers (valid flag)
     std::vector<UpcatTmaLayer> upt;       // per op; TMA-staged fused upsample+concat+depthwise
     bool use_dw_tma = true;
@@ -108,6 +110,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                     rc = conv_mma_launch(e->mma[i], batch, b0, s);
                     break;
                 }
+                if (op.flags & FLAG_XF) {
+                    rc = xf_launch(e->xf[i], batch, b0, e->num_sms, s);
+                    break;
+                }
                 if (op.flags & FLAG_TC) {
                     rc = tc_launch(e->tc[i], batch, b0, e->num_sms, s);
                     break;
@@ -135,6 +141,7 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 rc = launch_dwconv(a, s);
                 break;
             }
+            case OP_DWPW: rc = xf_launch(e->xf[i], batch, b0, e->num_sms, s); break;
             case OP_MAXPOOL2: rc = launch_maxpool2(in0, out0, batch, s); break;
             case OP_RESIZE_NEAREST: rc = launch_resize_nearest(in0, out0, batch, s); break;
             case OP_UPSAMPLE_BILINEAR2X: rc = launch_bilinear2x(in0, out0, batch, s); break;
@@ -260,7 +267,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
     e->tc.resize(n_ops);
     for (int i = 0; i < n_ops; ++i) {
         const OpDesc& op = e->ops[i];
-        if (op.type != OP_CONV || !(op.flags & FLAG_TC)) continue;
+        if (op.type != OP_CONV || !(op.flags & FLAG_TC) || (op.flags & FLAG_XF)) continue;
         TView in0 = resolve(e, op.in[0]), res = resolve(e, op.in[1]), out0 = resolve(e, op.out[0]);
         if (in0.fmt != DT_SPLIT16 || in0.c_stride != 1 || op.in[2].buf >= 0 || op.sh != op.sw) {
             set_error("op %d: tensor-core conv needs a SPLIT16 unit-stride input and no gate", i);
@@ -284,6 +291,37 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
             snprintf(tmp, sizeof(tmp), "%s", get_error());
             set_error("op %d: %s", i, tmp);
             return fail("tc");
+        }
+    }
+    // fused producer -> pointwise conv layers (conv_xf.cu): depthwise / up-sample+concat+depthwise / squeeze-excite scale
+    e->xf.resize(n_ops);
+    for (int i = 0; i < n_ops; ++i) {
+        const OpDesc& op = e->ops[i];
+        const bool dwpw = op.type == OP_DWPW, scale = op.type == OP_CONV && (op.flags & FLAG_XF);
+        if (!dwpw && !scale) continue;
+        XfSetup s;
+        memset(&s, 0, sizeof(s));
+        s.mode = dwpw ? XF_DW : XF_SCALE;
+        s.max_batch = max_batch;
+        s.x = resolve(e, op.in[0]);
+        s.res = resolve(e, op.in[1]);
+        if (dwpw) {
+            s.low = resolve(e, op.in[2]);
+            s.dww = e->d_weights + op.i[3];
+            s.dw_act = (int)op.f[1];
+        } else {
+            s.gate = resolve(e, op.in[2]);
+        }
+        s.out = resolve(e, op.out[0]);
+        s.Cout = s.out.C; s.act = op.act; s.n_tile = op.i[0]; s.n_tiles = op.i[1]; s.out_scale = op.f[0];
+        s.w_hi = e->d_weights + op.w_off; s.w_lo = e->d_weights + op.i[2];
+        s.bias = op.b_off >= 0 ? e->d_weights + op.b_off : nullptr;
+        s.res_first = (op.flags & FLAG_RES_FIRST) ? 1 : 0;
+        if (xf_prepare(e->xf[i], s)) {
+            char tmp[900];
+            snprintf(tmp, sizeof(tmp), "%s", get_error());
+            set_error("op %d: %s", i, tmp);
+            return fail("xf");
         }
     }
     // depthwise layers: TMA descriptors over the input views

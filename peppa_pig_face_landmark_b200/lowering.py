@@ -568,6 +568,16 @@ class _Lowerer:
         # any other map: ragged bw x 128/bw tiles (mirrors csrc/conv_tc.cu tc_pick_bw); SKPS_TC_ANY_W=0 turns them off
         return os.environ.get("SKPS_TC_ANY_W", "1") != "0" and any(bw <= W + 7 and 128 // bw <= H + 7 for bw in (64, 32, 16, 8))
 
+    def _xf_scale_ok(self, xin, gate, out_v, k, s, cout):
+        """Mirror of csrc/conv_xf.cu xf_supported() for XF_SCALE: 1x1 stride-1 conv, one N tile, 16x8 pixel tiles."""
+        if os.environ.get("SKPS_XF", "1") == "0" or os.environ.get("SKPS_XF_SCALE", "1") == "0":
+            return False
+        if list(k) != [1, 1] or list(s) != [1, 1] or P.tc_tiling(cout)[1] != 1:
+            return False
+        if gate.c_stride != 1 or (gate.buf.C | gate.c_off) % 4 or gate.buf.dtype != P.DT_F32:
+            return False
+        return xin.H >= 8 and xin.W >= 16 and -(-xin.C // 64) <= 16 and out_v.c_stride == 1
+
     def _conv_input(self, name):
         """Resolve a conv's input: plain view, or (view, gate view) for an SE-scaled tensor."""
         t = self.t[name]
@@ -620,7 +630,12 @@ class _Lowerer:
                              name=n.name)
                 elif self._tc_eligible(xin, k, s, p, d, flags, out_v.C, gate):
                     # tcgen05 path (csrc/conv_tc.cu): float16 hi/lo operands, input buffer in SPLIT16 format
-                    if gate is not None:
+                    xf_flag = 0
+                    if gate is not None and self._xf_scale_ok(xin, gate, out_v, k, s, w.shape[0]):
+                        # squeeze-excite scale applied to the A tiles in shared memory by the conv kernel itself
+                        # (csrc/conv_xf.cu, XF_SCALE): the expanded tensor is read once, no separate scale pass
+                        xf_flag = P.FLAG_XF
+                    elif gate is not None:
                         # squeeze-excite scale cannot ride on a TMA-fed operand: apply it in its own pass
                         sb = pl.new_buf(xin.C, xin.H, xin.W, P.DT_SPLIT16, n.name + ":se_scaled")
                         sv = P.View(sb, 0, 1, xin.C)
@@ -640,8 +655,8 @@ class _Lowerer:
                     n_tile, n_tiles = P.tc_tiling(wk_tc.shape[0])
                     hi, lo, out_scale = P.pack_tc_weights(wk_tc, n_tile, n_tiles)
                     b = b_tc
-                    o = P.Op(P.OP_CONV, [xin, res, None], [out_v], f["act"], k, s, p[:2], d, hi, b,
-                             flags | P.FLAG_TC, ints=[n_tile, n_tiles, 0, 0], floats=[out_scale], name=n.name)
+                    o = P.Op(P.OP_CONV, [xin, res, gate if xf_flag else None], [out_v], f["act"], k, s, p[:2], d, hi, b,
+                             flags | P.FLAG_TC | xf_flag, ints=[n_tile, n_tiles, 0, 0], floats=[out_scale], name=n.name)
                     o.w2 = lo
                 else:
                     o = P.Op(P.OP_CONV, [xin, res, gate], [out_v], f["act"], k, s, p[:2], d, wk, b, flags,
@@ -894,6 +909,68 @@ def _fuse_se_chain(pl):
         pl.ops.remove(gap)
 
 
+def _fuse_dw_pw(pl):
+    """depthwise 3x3 (stride 1) [or the fused upsample+concat+depthwise] -> 1x1 conv becomes one OP_DWPW when the depthwise
+    output has no other reader: transform warps of csrc/conv_xf.cu build the conv's A tiles in shared memory, the
+    depthwise output never reaches HBM.  MobileNetV3 blocks without squeeze-excite (kps_student.onnx blocks.0.0, 1.1,
+    3.1-3.3: conv_dw -> conv_pw[l]) and both DecoderBlock heads (model.py:133-196)."""
+    if os.environ.get("SKPS_XF", "1") == "0" or os.environ.get("SKPS_XF_DW", "1") == "0":
+        return
+
+    def same(a, b):
+        return a is not None and b is not None and a.buf is b.buf and (a.c_off, a.c_stride, a.C) == (b.c_off, b.c_stride, b.C)
+
+    def ok8(v):
+        return v.c_stride == 1 and not ((v.C | v.buf.C | v.c_off) & 7)
+
+    for d in list(pl.ops):
+        up = d.type == P.OP_UPCAT_DW
+        if not up and not (d.type == P.OP_DWCONV and list(d.k) == [3, 3] and list(d.s) == [1, 1] and list(d.d) == [1, 1]
+                           and list(d.p) == [1, 1] and not (d.flags & P.FLAG_GAP_PARTIAL)):
+            continue
+        mid = d.outs[0]
+        readers = [o for o in pl.ops if o is not d and any(v is not None and v.buf is mid.buf for v in o.ins)]
+        writers = [o for o in pl.ops if o is not d and any(v.buf is mid.buf for v in o.outs)]
+        if len(readers) != 1 or writers or mid.buf in [v.buf for v in pl.outputs]:
+            continue
+        c = readers[0]
+        if c.type != P.OP_CONV or list(c.k) != [1, 1] or list(c.s) != [1, 1] or not same(c.ins[0], mid) \
+                or c.ins[2] is not None or (c.flags & (P.FLAG_MMA | P.FLAG_XF | P.FLAG_IN_U8)):
+            continue
+        out = c.outs[0]
+        x = d.ins[1] if up else d.ins[0]
+        low = d.ins[0] if up else None
+        if not ok8(x) or x.buf.dtype not in (P.DT_F32, P.DT_SPLIT16) or out.H < 8 or out.W < 16:
+            continue
+        if up and (not ok8(low) or low.buf.dtype != P.DT_F32 or x.buf.dtype != P.DT_SPLIT16 or low.C % 64
+                   or out.H % 8 or out.W % 16):
+            continue
+        K = x.C + (low.C if up else 0)
+        n_tile, n_tiles = P.tc_tiling(out.C)
+        if n_tiles != 1 or -(-K // 64) > 16:
+            continue
+        if c.flags & P.FLAG_TC:
+            hi, lo, out_scale = c.w, c.w2, c.floats[0]
+            n_tile = c.ints[0]
+            bias = c.b
+        else:
+            hi, lo, out_scale = P.pack_tc_weights(c.w_ref, n_tile, n_tiles)
+            bias = c.b if c.b is not None else np.zeros(out.C, np.float32)
+        kpad = -(-K // 64) * 64
+        dww = np.zeros((10, kpad), np.float32)
+        dww[:9, :K] = d.w
+        dww[9, :K] = d.b
+        o = P.Op(P.OP_DWPW, [x, c.ins[1], low], [out], c.act, (1, 1), (1, 1), (0, 0), (1, 1), hi, bias,
+                 (c.flags & P.FLAG_RES_FIRST) | P.FLAG_TC, ints=[n_tile, 1, 0, 0], floats=[out_scale, float(d.act)],
+                 name=d.name + "+" + c.name.split("/")[-2] if "/" in c.name else d.name + "+pw")
+        o.w2 = lo
+        o.extra, o.extra_slot = dww, 3
+        o.w_ref, o.dw_w, o.dw_b, o.dw_act = c.w_ref, d.w, d.b, d.act
+        out.buf.dtype = out.buf.dtype            # the output keeps the format its readers asked for
+        pl.ops[pl.ops.index(c)] = o
+        pl.ops.remove(d)
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -904,6 +981,8 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     _fuse_upsample_concat_dw(lw.plan)
     if os.environ.get("SKPS_SE_FUSE", "1") != "0":
         _fuse_se_chain(lw.plan)
+    if use_tc:
+        _fuse_dw_pw(lw.plan)
     chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
     if chunk_env not in ("0", ""):
         lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)

@@ -30,6 +30,7 @@ OP_SCALE_CH = 12      # x * gate[n,c]  (squeeze-excite applied ahead of a tensor
 OP_UPCAT_DW = 13      # depthwise3x3(concat(bilinear_x2(low), skip)) without materialising the up-sampled tensor
 OP_ADDN = 14          # act(sum of up to 4 inputs), each optionally nearest-upsampled by 2^k (HRNet fuse layers)
 OP_SE_FC = 15         # squeeze-excite gate: per-tile channel sums -> mean -> 1x1 -> act -> 1x1 -> act  (N,1,1,C)
+OP_DWPW = 16          # act(conv1x1(dw_act(depthwise3x3(x | concat(bilinear_x2(low), x))))): the depthwise output lives in smem only (csrc/conv_xf.cu)
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}
 
@@ -88,7 +89,8 @@ class Op:
         self.flags, self.ints, self.floats, self.name = flags, list(ints), list(floats), name
         self.w_off = self.b_off = -1
         self.w2 = None                       # FLAG_TC: lo-plane weight matrix; its blob offset goes to ints[2]
-        self.extra = None                    # op-specific float32 table; its blob offset goes to ints[0] (OP_UPCAT_DW)
+        self.extra = None                    # op-specific float32 table; its blob offset goes to ints[extra_slot]
+        self.extra_slot = 0
 
     def __repr__(self):
         return "%s %s -> %s act=%d k=%s s=%s d=%s %s" % (OP_NAMES[self.type], self.ins, self.outs,
@@ -99,6 +101,7 @@ FLAG_IN_U8 = 1        # conv reads uint8 input and divides by 255 (first layer)
 FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo matrix (float16 bytes in the blob)
 FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
 FLAG_MMA = 16         # 3x3 conv with few channels on the halo-tile mma.sync kernel (csrc/conv_mma.cu): w = packed fp16 hi/lo
+FLAG_XF = 32          # tensor-core 1x1 conv whose input is scaled by ins[2] = gate[n,c] inside the kernel (csrc/conv_xf.cu, XF_SCALE)
 FLAG_GAP_PARTIAL = 8  # depthwise conv also writes per-tile channel sums of its output to outs[1] ([tiles][C] per sample)
 DW_TILE_W = 16
 
@@ -158,7 +161,9 @@ class Plan:
                 op.w_off = put(op.w) if op.w is not None else -1
             op.b_off = put(op.b) if op.b is not None else -1
             if op.extra is not None:
-                op.ints = [put(op.extra)] + list(op.ints[1:])
+                ints = list(op.ints) + [0] * (4 - len(op.ints))
+                ints[op.extra_slot] = put(op.extra)
+                op.ints = ints
         # tail slack: kernels that read weight rows in whole 16-byte / 64-channel pieces never run past the allocation
         parts.append(np.zeros(256, np.float32))
         return np.concatenate(parts)

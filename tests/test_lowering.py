@@ -113,12 +113,24 @@ def test_onnx_writer_round_trips_the_shipped_graphs(tmp_path):
 
 
 def test_student_plan_fusions():
-    """The fusions the student plan relies on: 8 squeeze-excite chains (GAP + 2 FC -> per-tile sums + one gate op),
-    both decoder heads (upsample + concat + depthwise), the split heat-map head."""
+    """The fusions the student plan relies on: 8 squeeze-excite chains (GAP + 2 FC -> per-tile sums + one gate op) whose
+    scale rides inside the projection conv (FLAG_XF, no OP_SCALE_CH pass), both decoder heads (upsample + concat +
+    depthwise + 1x1 as one OP_DWPW), the depthwise -> 1x1 pairs of the blocks without squeeze-excite, the split heat-map
+    head."""
     from peppa_pig_face_landmark_b200 import lowering, plan as P
     plan = lowering.lower(os.path.join(PRE, "kps_student.onnx"), (256, 256))
     kinds = [o.type for o in plan.ops]
-    assert kinds.count(P.OP_SE_FC) == 8 and kinds.count(P.OP_UPCAT_DW) == 2 and kinds.count(P.OP_GAP) == 2
+    assert kinds.count(P.OP_SE_FC) == 8 and kinds.count(P.OP_GAP) == 2
+    assert kinds.count(P.OP_UPCAT_DW) == 0 and kinds.count(P.OP_SCALE_CH) == 0
+    fused = [o for o in plan.ops if o.type == P.OP_DWPW]
+    assert len(fused) == 7 and sum(1 for o in fused if o.ins[2] is not None) == 2          # 5 encoder pairs + 2 decoder heads
+    for o in fused:
+        K = o.ins[0].C + (o.ins[2].C if o.ins[2] is not None else 0)
+        assert o.extra.shape == (10, -(-K // 64) * 64) and o.extra_slot == 3 and o.w.shape[1] == o.extra.shape[1]
+    scaled = [o for o in plan.ops if o.type == P.OP_CONV and o.flags & P.FLAG_XF]
+    assert len(scaled) == 8 and all(o.ins[2] is not None and o.ins[0].buf.dtype == P.DT_SPLIT16 for o in scaled)
+    for o in scaled:                     # each gate comes from the squeeze-excite op of the same block
+        assert any(se.outs[0].buf is o.ins[2].buf for se in plan.ops if se.type == P.OP_SE_FC)
     for se in (o for o in plan.ops if o.type == P.OP_SE_FC):
         dw = [o for o in plan.ops if o.type == P.OP_DWCONV and len(o.outs) == 2 and o.outs[1].buf is se.ins[0].buf]
         assert len(dw) == 1 and dw[0].flags & P.FLAG_GAP_PARTIAL
