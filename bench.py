@@ -119,40 +119,61 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_faces_per_s(n_faces, seed=0):
-    """Reference CPU path for this workload: the batch-1 loop of face_landmark.py:40-48 on the oracle's
-    torch-CPU executor of the same ONNX graph (onnxruntime is absent from this image)."""
-    import torch
-    import frames
-    from oracle.faceana_ref import LandmarkRef
-    torch.set_num_threads(host_cores())
-    crops = frames.noise_crops(n_faces, seed=seed)
-    ref = LandmarkRef()
-    ref.forward_crops(crops[:2])                       # warm-up
-    t0 = time.perf_counter()
-    ref.forward_crops(crops)
-    dt = time.perf_counter() - t0
-    return n_faces / dt, dt
+REF_LABEL = ("oracle port of the reference CPU path: batch-1 loop of face_landmark.py:40-48 on a node-by-node torch-CPU "
+             "executor of kps_student.onnx (onnxruntime, the reference's engine, is absent from this image)")
+
+
+class CpuReference:
+    """The reference's CPU path for this workload.  Built ONCE (ONNX parse + weight conversion stay outside every
+    timed region); `rate(n)` times only forward_crops on n faces."""
+
+    def __init__(self):
+        import torch
+        import frames
+        from oracle.faceana_ref import LandmarkRef
+        torch.set_num_threads(host_cores())
+        self.frames = frames
+        self.ref = LandmarkRef()
+        self.ref.forward_crops(frames.noise_crops(2, seed=7))          # first-call allocations, thread pool start-up
+
+    def rate(self, n_faces, seed=0):
+        crops = self.frames.noise_crops(n_faces, seed=seed)
+        t0 = time.perf_counter()
+        self.ref.forward_crops(crops)
+        dt = time.perf_counter() - t0
+        return n_faces / dt, dt
+
+
+def workload_config(B):
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "input": "uint8 256x256x3 crops",
+            "l2": "inputs rotate over 4 x 50 MB sets (> 126 MB L2); activations per batch exceed L2"}
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  One step = the
+    batch-1 loop over one batch of crops; the batch is the full 256 faces when K+W steps of it fit ~150 s at the measured
+    rate, else the largest power-of-two fraction that does (stated in cpu_baseline.sample)."""
     if rank != 0:
         return
-    sample = 24
-    for _ in range(args.warmup):
-        cpu_reference_faces_per_s(4)
-    t0 = time.perf_counter()
+    cpu = CpuReference()
+    v0, _ = cpu.rate(8)
+    budget_s = 150.0
+    sample = args.batch
+    while sample > 8 and (args.steps + args.warmup) * sample / v0 > budget_s:
+        sample //= 2
+    for k in range(args.warmup):
+        cpu.rate(sample, seed=1000 + k)
+    dt = 0.0
     for k in range(args.steps):
-        cpu_reference_faces_per_s(sample, seed=k)
-    dt = time.perf_counter() - t0
+        dt += cpu.rate(sample, seed=k)[1]                   # only forward_crops is inside the clock
     fps = args.steps * sample / dt
     line = {
         "impl": "reference", "metric": "faces/sec Student@256 batch=256", "value": fps, "unit": "faces/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_faces_per_step": sample},
+        "config": workload_config(args.batch),
         "cpu_baseline": {"value": fps, "unit": "faces/s", "cores": host_cores(), "kind": "port",
-                         "sample": "%d faces per step, batch-1 loop, torch-CPU executor of kps_student.onnx" % sample},
+                         "sample": "%d of %d faces per step, %d steps; %s" % (sample, args.batch, args.steps, REF_LABEL)},
         "e2e": {"value": fps, "unit": "faces/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -185,9 +206,19 @@ def main():
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its version banner there)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version/INFO banner to fd 1 when the communicator is created; stdout must carry exactly one JSON
+        # line, so fd 1 points at stderr while the communicator comes up (the caller's NCCL_DEBUG is left untouched)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B = args.batch
     onnx = os.path.join(ROOT, "peppa_pig_face_landmark_b200", "pretrained", "kps_student.onnx")
     eng = ONNXEngine(onnx, device="cuda:%d" % local_rank, max_batch=B)
@@ -267,63 +298,92 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (largest conv by MACs), timed alone with CUDA events
+    # ---- per-op times (each op launched alone, CUDA events on the launching stream): roofline of the dominant
+    # tensor-bound kernel (largest conv by MACs) and of the slowest HBM-bound kernel, plus the time split by op class
     from peppa_pig_face_landmark_b200 import plan as P
-    best, best_macs = None, 0
-    for idx, op in enumerate(eng.plan.ops):
-        if op.type == P.OP_CONV:
-            o = op.outs[0]
-            macs = o.C * o.H * o.W * op.ins[0].C * op.k[0] * op.k[1]
-            if macs > best_macs:
-                best, best_macs = idx, macs
-    reps = 10
-    with torch.cuda.stream(stream):
-        for _ in range(3):
-            rt.check(lib.skps_engine_run_op(eng.handle, best, B, stream.cuda_stream))
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
-        for _ in range(reps):
-            rt.check(lib.skps_engine_run_op(eng.handle, best, B, stream.cuda_stream))
-        k1.record()
-    torch.cuda.synchronize()
-    k_ms = k0.elapsed_time(k1) / reps
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    bop = eng.plan.ops[best]
-    k_flops = 2.0 * best_macs * B
-    achieved_tf = k_flops / (k_ms * 1e-3) / 1e12
+
+    def conv_macs(op):
+        if op.type == P.OP_CONV:
+            return op.outs[0].C * op.outs[0].H * op.outs[0].W * op.ins[0].C * op.k[0] * op.k[1]
+        if op.type == P.OP_DWPW:
+            return op.outs[0].C * op.outs[0].H * op.outs[0].W * op.w.shape[1]
+        return 0
+
+    def time_op(idx, reps):
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                rt.check(lib.skps_engine_run_op(eng.handle, idx, B, stream.cuda_stream))
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            for _ in range(reps):
+                rt.check(lib.skps_engine_run_op(eng.handle, idx, B, stream.cuda_stream))
+            k1.record()
+        torch.cuda.synchronize()
+        return k0.elapsed_time(k1) / reps
+
+    op_ms = [time_op(i, 5) for i in range(len(eng.plan.ops))]
+    split = {}
+    for op, t in zip(eng.plan.ops, op_ms):
+        kind = P.OP_NAMES[op.type] + ("/xf_scale" if op.flags & P.FLAG_XF else "/tc" if op.flags & P.FLAG_TC else "")
+        split[kind] = split.get(kind, 0.0) + t
+    best = max(range(len(eng.plan.ops)), key=lambda i: conv_macs(eng.plan.ops[i]) if eng.plan.ops[i].type == P.OP_CONV else 0)
+    bop, best_macs = eng.plan.ops[best], conv_macs(eng.plan.ops[best])
+    k_ms = time_op(best, 10)
+    achieved_tf = 2.0 * best_macs * B / (k_ms * 1e-3) / 1e12
     log("dominant kernel %.3f ms -> %.2f TFLOP/s" % (k_ms, achieved_tf))
-    bop = eng.plan.ops[best]
-    # DRAM traffic of this launch from the committed `ncu --set full` capture (dram__bytes_read.sum +
-    # dram__bytes_write.sum, profiles/r1_ncu_conv_tc_tail_v3.txt); only valid for the batch-256 conv2 launch
-    traffic = 0.538947e9 + 0.487993e9 if (B == 256 and bop.k[0] == 3 and bop.ins[0].C == 128 and bop.outs[0].C == 128) else None
+    # DRAM traffic of the dominant launch: read from the committed `ncu --set full` summary of THIS kernel (same op, same
+    # batch); null when no matching capture is on file
+    traffic, traffic_src = None, None
+    try:
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_conv2_final.json")))
+        if cap["op"] == bop.name and cap["batch"] == B:
+            traffic = cap["dram__bytes_read"] + cap["dram__bytes_write"]
+            traffic_src = "profiles/r2_ncu_conv2_final.json (%s)" % cap["capture"]
+    except Exception:
+        pass
+    # slowest kernel that is bound by HBM (no dense contraction): algorithmic bytes = its input + output tensors
+    hb = max((i for i, op in enumerate(eng.plan.ops) if conv_macs(op) == 0 and op.type != P.OP_HM_DECODE),
+             key=lambda i: op_ms[i])
+    hop = eng.plan.ops[hb]
+    h_bytes = eng.plan.bytes_per_sample(hop) * B
+    h_gbs = h_bytes / (op_ms[hb] * 1e-3) / 1e9
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "traffic_algorithmic": 2 * B * bop.outs[0].H * bop.outs[0].W * 128 * 4,
+                "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_algorithmic": B * eng.plan.bytes_per_sample(bop),
                 "precision": "fp16 hi/lo split, 3 tcgen05 MMAs per K-step -> ceiling = peak/3",
                 "frac_of_split_ceiling": achieved_tf / (peak_tf / 3.0),
                 "kernel": "%s (%dx%d conv %d->%d @%dx%d, batch %d)" % (bop.name, bop.k[0], bop.k[1], bop.ins[0].C,
                                                                      bop.outs[0].C, bop.outs[0].H, bop.outs[0].W, B),
                 "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms / args.steps),
                 "peak_source": "%s bf16 dense burst (MEASURED_PEAKS.json)" % peak_src,
+                "hbm_kernel": {"bound": "hbm", "kernel": "%s %s (%d ch @%dx%d, batch %d)" % (
+                                   P.OP_NAMES[hop.type], hop.name, hop.outs[0].C, hop.outs[0].H, hop.outs[0].W, B),
+                               "achieved": h_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": h_gbs / peak_hbm,
+                               "bytes_algorithmic": h_bytes, "kernel_ms": op_ms[hb],
+                               "kernel_share_of_step": op_ms[hb] / (ms / args.steps)},
+                "op_class_ms": {k: round(v, 4) for k, v in sorted(split.items(), key=lambda kv: -kv[1])},
+                "op_sum_ms": sum(op_ms),
                 "whole_net_tflops": faces_per_s / world * STUDENT_FLOP_PER_FACE / 1e12,
                 "whole_net_frac_2mac": faces_per_s / world * STUDENT_FLOP_PER_FACE / 1e12 / peak_tf,
+                "whole_net_frac_of_split_ceiling": faces_per_s / world * STUDENT_FLOP_PER_FACE / 1e12 / (peak_tf / 3.0),
                 "whole_net_frac_readme_1.39G": faces_per_s / world * STUDENT_README_GFLOP / 1e12 / peak_tf}
 
     cpu = None
     if not args.no_cpu_baseline:
         log("cpu baseline on %d host threads" % host_cores())
-        v1, dt1 = cpu_reference_faces_per_s(8)
+        ref = CpuReference()
+        v1, _ = ref.rate(8)
         n = int(max(8, min(256, 12.0 * v1)))          # ~12 s of CPU work
-        v, dt = cpu_reference_faces_per_s(n)
+        v, dt = ref.rate(n, seed=1)
         cpu = {"value": v, "unit": "faces/s", "cores": host_cores(), "kind": "port",
-               "sample": "%d faces, batch-1 loop (face_landmark.py:40-48), torch-CPU executor, %.1f s" % (n, dt)}
+               "sample": "%d faces in %.1f s; %s" % (n, dt, REF_LABEL)}
 
     line = {
         "metric": "faces/sec Student@256 batch=256", "value": faces_per_s, "unit": "faces/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "input": "uint8 256x256x3 crops",
-                   "l2": "inputs rotate over 4 x 50 MB sets (> 126 MB L2); activations per batch exceed L2"},
+        "config": workload_config(B),
         "e2e": {"value": e2e_fps, "unit": "faces/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "ONNXEngine.stream_u8 (pinned host crops in, host landmarks+scores out, 2 batches in flight: H2D of step i+1 overlaps compute of step i)"},
         "gpu_launches": lib.skps_engine_launches_for_batch(eng.handle, B) * args.steps,

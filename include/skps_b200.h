@@ -206,6 +206,9 @@ SKPS_API int skps_pipeline_run(skps_pipeline* p, const uint8_t* frame, int H, in
  * returns -1.0 in *mean_diff when there is no previous frame of the same size. */
 SKPS_API int skps_pipeline_frame_diff(skps_pipeline* p, const uint8_t* frame, int H, int W,
                              int frame_on_device, double* mean_diff, void* stream);
+/* Adopt the frame staged by skps_pipeline_frame_diff as the previous frame without running the chain: the skip path of
+ * FaceAna.run (facer.py:57-62 replaces previous_image on every call, also when nothing is detected or tracked). */
+SKPS_API int skps_pipeline_commit_frame(skps_pipeline* p, int H, int W);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,8 @@ class FaceDetector:
                                            s.cuda_stream))
         s.synchronize()
         n = int(self._count.item())
+        if n < 0:
+            raise RuntimeError("FaceDetector: %d candidates over the score threshold (the NMS kernel ranks at most 1024)" % -n)
         bboxes = self._kept[:n].cpu().numpy()
         self.last_keep_idx = self._idx[:n].cpu().numpy().astype(np.int64)
         logger.info('detect done, time consume: %.5f' % (time.time() - t0))

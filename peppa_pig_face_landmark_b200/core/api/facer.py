@@ -94,6 +94,7 @@ class FaceAna():
             # facer.py:61 with an empty/None track: nothing to do (the reference would fail on None)
             boxes_return = np.zeros((0, 4), np.float32)
             landmarks, states = np.array([]), np.array([])
+            rt.check(self.lib.skps_pipeline_commit_frame(self._pipe, H, W))     # the staged frame is the new "previous"
         else:
             rt.check(self.lib.skps_pipeline_run(
                 self._pipe, None, H, W, 0, 1 if run_det else 0, rw, rh, top, left, float(scale),

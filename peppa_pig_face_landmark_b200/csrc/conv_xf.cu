@@ -685,6 +685,8 @@ static int xf_launch_m(const XfLayer& L, const XfK& k, int grid, cudaStream_t st
     switch (k.act) {
         case ACT_NONE: return sp ? xf_launch_t<MODE, ACT_NONE, true>(L, k, grid, stream) : xf_launch_t<MODE, ACT_NONE, false>(L, k, grid, stream);
         case ACT_RELU: return sp ? xf_launch_t<MODE, ACT_RELU, true>(L, k, grid, stream) : xf_launch_t<MODE, ACT_RELU, false>(L, k, grid, stream);
+        case ACT_HSWISH: return sp ? xf_launch_t<MODE, ACT_HSWISH, true>(L, k, grid, stream) : xf_launch_t<MODE, ACT_HSWISH, false>(L, k, grid, stream);
+        case ACT_SILU: return sp ? xf_launch_t<MODE, ACT_SILU, true>(L, k, grid, stream) : xf_launch_t<MODE, ACT_SILU, false>(L, k, grid, stream);
         default: break;
     }
     set_error("conv_xf: activation %d not instantiated", k.act);

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
 
 // ------------------------------------------------------------------------------------------
 // Detector post-processing (face_detector.py:31-37, 73-136).  One block.
-//   1. rows with obj > score_thres -> xyxy candidates (cap MAXC)
+//   1. rows with obj > score_thres -> xyxy candidates (more than MAXC: count = -candidates, nothing else written)
 //   2. order = (score desc, row index desc)  [np.argsort(score)[::-1]; ties measure-zero]
 //   3. greedy NMS: survivors are those with iou < iou_thres against every kept box
 //   4. kept rows copied out with cols 0-3 mapped back: (v - pad) / scale
@@ -178,7 +178,13 @@ __global__ void __launch_bounds__(1024) detect_post_kernel(const float* __restri
         }
     }
     __syncthreads();
-    const int n = min(s_n, MAXC);
+    if (s_n > MAXC) {
+        // more candidates than the kernel can rank: refuse (count = -candidates) rather than drop an order-dependent subset;
+        // the host raises.  The reference has no cap (face_detector.py:95-136); 1024 rows over obj 0.5 is a noise frame.
+        if (tid == 0) *count = -s_n;
+        return;
+    }
+    const int n = s_n;
     // rank sort: key (score desc, row desc) is a total order, so the result is deterministic
     for (int i = tid; i < n; i += nt) {
         float si = s_score[i];

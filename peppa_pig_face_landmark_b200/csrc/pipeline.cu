@@ -105,8 +105,8 @@ extern "C" SKPS_API int skps_pipeline_reset(skps_pipeline* p) {
 // Upload (or adopt) the frame into d_frame[cur]; returns the device pointer.
 static int stage_frame(skps_pipeline* p, const uint8_t* frame, int H, int W, int on_device, cudaStream_t s,
                        const uint8_t** dptr) {
-    SKPS_CHECK(H > 0 && W > 0 && H <= p->cfg.max_h && (size_t)H * W <= (size_t)p->cfg.max_h * p->cfg.max_w,
-               "frame %dx%d larger than the pipeline maximum %dx%d", H, W, p->cfg.max_h, p->cfg.max_w);
+    SKPS_CHECK(H > 0 && W > 0 && (size_t)H * W <= (size_t)p->cfg.max_h * p->cfg.max_w,
+               "frame %dx%d has more pixels than the pipeline maximum %dx%d", H, W, p->cfg.max_h, p->cfg.max_w);
     size_t bytes = (size_t)H * W * 3;
     if (on_device) {
         SKPS_CUDA(cudaMemcpyAsync(p->d_frame[p->cur], frame, bytes, cudaMemcpyDeviceToDevice, s));
@@ -142,6 +142,15 @@ extern "C" SKPS_API int skps_pipeline_frame_diff(skps_pipeline* p, const uint8_t
     SKPS_CUDA(cudaStreamSynchronize(s));
     // facer.py:113: np.sum(diff)/H/W/3.
     *mean_diff = (double)p->h_res->diff / (double)H / (double)W / 3.0;
+    return 0;
+}
+
+// The frame staged by skps_pipeline_frame_diff becomes the "previous" frame without running the chain (FaceAna.run on
+// a static frame with nothing to track, facer.py:57-62: previous_image is replaced every frame).
+extern "C" SKPS_API int skps_pipeline_commit_frame(skps_pipeline* p, int H, int W) {
+    SKPS_CHECK(p && H > 0 && W > 0, "commit_frame: bad arguments");
+    p->prev_h = H; p->prev_w = W;
+    p->cur ^= 1;
     return 0;
 }
 
@@ -198,12 +207,14 @@ extern "C" SKPS_API int skps_pipeline_run(skps_pipeline* p, const uint8_t* frame
     SKPS_CUDA(cudaMemcpyAsync(p->h_kps, p->d_kps, sizeof(float) * 2 * P * K, cudaMemcpyDeviceToHost, s));
     SKPS_CUDA(cudaMemcpyAsync(p->h_scores, skps_engine_output_ptr(p->kps, 1), sizeof(float) * P * K,
                               cudaMemcpyDeviceToHost, s));
+    if (run_detector) SKPS_CUDA(cudaMemcpyAsync(&p->h_res->n_det, p->d_det_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (run_detector && n_det) {
-        SKPS_CUDA(cudaMemcpyAsync(&p->h_res->n_det, p->d_det_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         SKPS_CUDA(cudaMemcpyAsync(p->h_det_idx, p->d_det_idx, sizeof(int32_t) * p->max_det, cudaMemcpyDeviceToHost, s));
         SKPS_CUDA(cudaMemcpyAsync(p->h_det_rows, p->d_det_rows, sizeof(float) * 16 * p->max_det, cudaMemcpyDeviceToHost, s));
     }
     SKPS_CUDA(cudaStreamSynchronize(s));
+    SKPS_CHECK(!run_detector || p->h_res->n_det >= 0, "detector produced %d candidates over the score threshold (limit 1024)",
+               -p->h_res->n_det);
     const int nf = p->h_res->n_faces;
     *n_faces = nf;
     memcpy(boxes4, p->h_boxes, sizeof(float) * 4 * nf);

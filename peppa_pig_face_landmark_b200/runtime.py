@@ -72,6 +72,7 @@ SIGNATURES = {
     "skps_pipeline_run": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_float, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                     c_vp]),
+    "skps_pipeline_commit_frame": (C.c_int, [c_vp, C.c_int, C.c_int]),
     "skps_pipeline_frame_diff": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), c_vp]),
 }
 
