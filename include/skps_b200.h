@@ -119,6 +119,14 @@ SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int H, int W, i
                                 const float* bias, int Cout, int act, int n_tile, float out_scale, const float* residual,
                                 int res_first, int out_split, float* out);
 
+/* Unit-test entries for two fused kernels that otherwise only run inside a whole network (csrc/debug_ops.cu):
+ * the squeeze-excite gate (mean of per-tile channel sums -> FC -> act -> FC -> act; kps_student.onnx .../se/ nodes) and the
+ * heat-map decode (arg-max + offsets, TRAIN/face_landmark/lib/core/base_trainer/model.py:511-554).  Host float32. */
+SKPS_API int skps_debug_se_fc(const float* part, int N, int tiles, int C, const float* w1t, const float* b1, const float* w2t,
+                              const float* b2, int Cr, int act1, int act2, int hw, float* gate);
+SKPS_API int skps_debug_hm_decode(const float* hm, int N, int H, int W, int ld, int npts, const float* feat, int K,
+                                  const float* w_off, const float* b_off, float* xy, float* score);
+
 /* Unit-test entry for the few-channel 3x3 convolution kernel (csrc/conv_mma.cu; Cin == Cout == C in {24, 40}, the
  * Teacher's HRNet branch convs): x, residual, out float32 NHWC; w_packed float16 [tap][hi/lo][C][C] as packed by
  * plan.pack_mma_weights. */

@@ -20,6 +20,7 @@ SOURCES = {
     "conv_mma.cu": [],
     "dw_tma.cu": [],
     "ops_misc.cu": [],
+    "debug_ops.cu": [],
     "image_ops.cu": ["-fmad=false"],     # float32/double expressions must round like numpy's
 }
 

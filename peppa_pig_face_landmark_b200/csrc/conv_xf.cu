@@ -56,6 +56,15 @@ __device__ __forceinline__ float4 f4_mix(const float wa, const float4 a, const f
     return make_float4(fmaf(wb, b.x, wa * a.x), fmaf(wb, b.y, wa * a.y), fmaf(wb, b.z, wa * a.z), fmaf(wb, b.w, wa * a.w));
 }
 
+template <int ACT>
+__device__ __forceinline__ void act16(float4* acc) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        acc[q].x = act_t<ACT>(acc[q].x); acc[q].y = act_t<ACT>(acc[q].y);
+        acc[q].z = act_t<ACT>(acc[q].z); acc[q].w = act_t<ACT>(acc[q].w);
+    }
+}
+
 template <int MODE, int ACT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(XF_THREADS, 1)
 conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1_hi,
@@ -355,11 +364,15 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                         if (++rst == p.rs) { rst = 0; rph ^= 1u; }
                         // activation, fp16 hi/lo split, store into the swizzled K-major A tile
                         const int jc = h * 4 + (cl >> 1);                    // logical 16-byte chunk of the 128-byte row
+                        switch (p.dw_act) {               // one branch per sub-chunk, not one per element
+                            case ACT_RELU: act16<ACT_RELU>(acc); break;
+                            case ACT_HSWISH: act16<ACT_HSWISH>(acc); break;
+                            case ACT_SILU: act16<ACT_SILU>(acc); break;
+                            default: break;
+                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            float4 v = acc[q];
-                            v.x = apply_act(v.x, p.dw_act); v.y = apply_act(v.y, p.dw_act);
-                            v.z = apply_act(v.z, p.dw_act); v.w = apply_act(v.w, p.dw_act);
+                            const float4 v = acc[q];
                             const int r = prow * XF_TW + xs + q;
                             split_store4(sa + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4) + (uint32_t)(cl & 1) * 8u, v);
                         }

@@ -21,16 +21,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint expires)
+// instead of re-issuing try_wait back to back.  Without the hint the spin loops of the waiting roles took 37 % of all issued
+// instructions of the fused kernel (profiles/r2_ncu_xf_up2_v1.txt) and starved the transform warps.
+constexpr uint32_t MBAR_SUSPEND_NS = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
 }
 // Bounded wait for kernels under development: traps (the launch fails with an error) instead of hanging the GPU when a
 // pipeline bug leaves a barrier incomplete for ~2 s.
@@ -41,11 +45,11 @@ __device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            "}\n" : "=r"(ok) : "r"(bar), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
         if (ok) return;
-        if ((it & 1023u) == 1023u) {
+        if ((it & 15u) == 15u) {
             uint64_t t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             if (t0 == 0) t0 = t;

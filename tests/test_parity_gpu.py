@@ -144,7 +144,7 @@ def test_onnxengine_contract_matches_oracle(oracle_nets, H):
     assert isinstance(out, list) and out[0].shape == (1, 15120, 16)
     ref = np.asarray(det_ref.net.run(x)[0]).reshape(15120, 16)
     assert np.array_equal(np.where(out[0][0][:, 4] > 0.5)[0], np.where(ref[:, 4] > 0.5)[0])
-    assert np.abs(out[0][0] - ref).max() < 5e-3
+    assert (np.abs(out[0][0] - ref) < 5e-3 + 2e-5 * np.abs(ref)).all()      # rows reach ~600 px: absolute + relative
     with pytest.raises(ValueError):
         eng(np.zeros((1, 3, 100, 100), np.float32))
     crops = frames.crop_variants(4)

@@ -1,5 +1,5 @@
 """Summarise an ncu launch list (gpu__time_duration.sum, one forward) per plan op:
-python tools/launch_table.py launches.csv [top] [student|teacher]"""
+python tools/launch_table.py launches.csv [top] [student|teacher|detector]"""
 import csv, sys, os
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
@@ -7,11 +7,14 @@ from collections import defaultdict
 from peppa_pig_face_landmark_b200 import lowering, plan as P
 path = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+model = sys.argv[3] if len(sys.argv) > 3 else "student"
 lines = [l for l in open(path) if not l.startswith('==')]
 rows = list(csv.DictReader(lines))
-if len(sys.argv) > 3 and sys.argv[3] == 'teacher':
+if model == 'teacher':
     from peppa_pig_face_landmark_b200 import teacher_graph
     pl = lowering.lower(teacher_graph.ensure_teacher_onnx(), (256, 256))
+elif model == 'detector':
+    pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/yolov5n-0.5.onnx'), (384, 640))
 else:
     pl = lowering.lower(os.path.join(ROOT, 'peppa_pig_face_landmark_b200/pretrained/kps_student.onnx'), (256, 256))
 ops = []
@@ -25,9 +28,10 @@ for i, (row, op) in enumerate(zip(rows, ops)):
     t = float(row['Metric Value']) / 1e3
     tot += t
     o = op.outs[0]
-    kind = P.OP_NAMES[op.type] + ('/TC' if op.flags & 2 else '')
+    kind = P.OP_NAMES[op.type] + ('/XF' if op.flags & P.FLAG_XF else '/TC' if op.flags & 2 else '')
     d[kind] += t
-    out.append((t, i, kind, op.ins[0].C, o.C, o.H, op.k[0], op.name[-44:]))
+    cin = op.w.shape[1] if op.type == P.OP_DWPW else op.ins[0].C
+    out.append((t, i, kind, cin, o.C, o.H, op.k[0], op.name[-44:]))
 print('total %.1f us over %d launches' % (tot, len(rows)))
 for x in sorted(out, reverse=True)[:top]:
     print('%9.1f us  #%-3d %-22s cin=%-4d cout=%-4d H=%-4d k=%d %s' % x)
