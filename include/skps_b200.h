@@ -117,7 +117,7 @@ SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, c
 SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int H, int W, int Cx, int x_split, const float* low, int Cl,
                                 const float* gate, const float* dww, int dw_act, const void* w_hi, const void* w_lo,
                                 const float* bias, int Cout, int act, int n_tile, float out_scale, const float* residual,
-                                int res_first, int out_split, float* out);
+                                int res_first, int out_split, float* out, const float* weff);
 
 /* Unit-test entries for two fused kernels that otherwise only run inside a whole network (csrc/debug_ops.cu):
  * the squeeze-excite gate (mean of per-tile channel sums -> FC -> act -> FC -> act; kps_student.onnx .../se/ nodes) and the
@@ -217,6 +217,29 @@ SKPS_API int skps_pipeline_frame_diff(skps_pipeline* p, const uint8_t* frame, in
 /* Adopt the frame staged by skps_pipeline_frame_diff as the previous frame without running the chain: the skip path of
  * FaceAna.run (facer.py:57-62 replaces previous_image on every call, also when nothing is detected or tracked). */
 SKPS_API int skps_pipeline_commit_frame(skps_pipeline* p, int H, int W);
+
+/* ---- FaceAna.run for many concurrent video streams (csrc/mpipe.cu) ---------------------------------
+ * What one FaceAna instance per stream does on the host in the reference (facer.py:52-85 with GroupTrack / OneEuroFilter /
+ * EmaFilter of Skps/core/smoother/lk.py:6-162) happens here for up to n_streams streams per call with all per-stream state
+ * on the device: one detector forward and one landmark forward per call, batched over the streams.
+ * det needs max_batch >= n_streams, kps needs max_batch >= n_streams * cfg->top_k.  Not thread-safe per handle. */
+typedef struct skps_mpipe skps_mpipe;
+SKPS_API int skps_mpipe_create(skps_engine* det, skps_engine* kps, const skps_pipeline_cfg* cfg, int n_streams,
+                               skps_mpipe** out);
+SKPS_API void skps_mpipe_destroy(skps_mpipe* p);
+/* FaceAna.reset() for one stream (or all: stream = -1): forget the previous frame, the track boxes, the landmark history. */
+SKPS_API int skps_mpipe_reset(skps_mpipe* p, int stream);
+SKPS_API int skps_mpipe_dims(const skps_mpipe* p, int* n_streams, int* top_k, int* n_points);
+/* Enqueue frame i (HxWx3 uint8 BGR, [host] pinned or pageable, or [dev]) of stream i for i < n; hw = {H0,W0,H1,W1,...}.
+ * slot in {0,1}: submit(0) submit(1) wait(0) submit(0) ... keeps two batches in flight (uploads overlap compute).
+ * Pinned frames must stay valid until skps_mpipe_wait(slot).  Asynchronous. */
+SKPS_API int skps_mpipe_submit(skps_mpipe* p, int slot, const uint8_t* const* frames, const int32_t* hw, int n,
+                               int frames_on_device);
+/* Block until the slot's results are in host memory.  Per stream s < n: n_faces[s]; boxes (n, top_k, 4) float64 = the
+ * refreshed track boxes (the 'box' entries of FaceAna.run); kps (n, top_k, n_points, 2) float64 smoothed landmarks;
+ * scores (n, top_k, n_points) float32; ran_detector[s] (may be NULL) = the frame-difference gate's decision. */
+SKPS_API int skps_mpipe_wait(skps_mpipe* p, int slot, int32_t* n_faces, double* boxes, double* kps, float* scores,
+                             int32_t* ran_detector);
 
 #ifdef __cplusplus
 }

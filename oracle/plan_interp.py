@@ -22,9 +22,19 @@ def _act(x, a):
     return x * hs if a == P.ACT_HSWISH else hs
 
 
+def split16_round(x, lo_scale=1.0):
+    """v -> hi + lo as the SPLIT16 activation format stores it: hi = fp16(v), lo = fp16((v - hi) * lo_scale) / lo_scale
+    (float16 subnormals included).  Used to measure what the format alone costs (tools/split_error.py)."""
+    hi = x.to(torch.float16).to(torch.float32)
+    lo = ((x - hi) * lo_scale).to(torch.float16).to(torch.float32) / lo_scale
+    return hi + lo
+
+
 class PlanInterp:
-    def __init__(self, plan):
+    def __init__(self, plan, emulate_split=False, lo_scale=1.0):
         self.plan = plan
+        self.emulate_split = emulate_split      # tensor-core convs: operands rounded to the fp16 hi/lo format, fp64 accumulate
+        self.lo_scale = lo_scale
 
     def run(self, x_nhwc, dump=None):
         """x: (N,H,W,3) uint8 (or float32 already /255 when the plan was lowered with input_u8=False)."""
@@ -53,8 +63,13 @@ class PlanInterp:
                 padc = op.outs[0].C - w.shape[0]          # zero-padded output channels (odd-width heat map)
                 if padc > 0:
                     w = torch.cat([w, torch.zeros((padc,) + tuple(w.shape[1:]))])
-                y = F.conv2d(x.permute(0, 3, 1, 2), w, bias,
-                             stride=op.s, padding=tuple(op.p), dilation=op.d)
+                if self.emulate_split and (op.flags & (P.FLAG_TC | P.FLAG_MMA)):
+                    sc = np.float32(1.0 / op.floats[0])                     # the weights' power-of-two pre-scale
+                    y = F.conv2d(split16_round(x, self.lo_scale).permute(0, 3, 1, 2).double(),
+                                 (split16_round(w * sc) / sc).double(), bias.double() if bias is not None else None,
+                                 stride=op.s, padding=tuple(op.p), dilation=op.d).float()
+                else:
+                    y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, stride=op.s, padding=tuple(op.p), dilation=op.d)
                 y = y.permute(0, 2, 3, 1)
                 if op.ins[1] is not None and (op.flags & P.FLAG_RES_FIRST):
                     y = _act(y + rd(op.ins[1]), op.act)          # conv-bn, += shortcut, relu

@@ -13,6 +13,9 @@ def __getattr__(name):
     if name == "FaceAna":
         from .core.api.facer import FaceAna
         return FaceAna
+    if name == "FaceAnaStreams":
+        from .core.api.streams import FaceAnaStreams
+        return FaceAnaStreams
     if name == "FaceDetector":
         from .core.api.face_detector import FaceDetector
         return FaceDetector
@@ -25,4 +28,4 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-__all__ = ["FaceAna", "FaceDetector", "FaceLandmark", "ONNXEngine"]
+__all__ = ["FaceAna", "FaceAnaStreams", "FaceDetector", "FaceLandmark", "ONNXEngine"]

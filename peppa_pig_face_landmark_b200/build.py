@@ -14,6 +14,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = {
     "engine.cu": [],
     "pipeline.cu": [],
+    "mpipe.cu": [],
+    "temporal.cu": ["-fmad=false"],  # float64 arithmetic must round like numpy's (no contraction)
     "conv_simt.cu": [],
     "conv_tc.cu": [],
     "conv_xf.cu": [],

@@ -30,7 +30,8 @@ struct OpDesc {          // 64 words
     int32_t i[4];
     float f[8];
     View in3;            // 4th input (OP_ADDN)
-    int32_t pad[64 - (2 + 30 + 8 + 3 + 4 + 8 + 6)];
+    int32_t i2[2];       // more blob offsets (OP_DWPW: [0] = class weights of the up-sampled channels)
+    int32_t pad[64 - (2 + 30 + 8 + 3 + 4 + 8 + 6 + 2)];
 };
 static_assert(sizeof(OpDesc) == 64 * 4, "OpDesc must be 64 words");
 

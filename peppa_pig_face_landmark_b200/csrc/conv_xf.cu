@@ -35,6 +35,7 @@ constexpr int XF_IW = XF_TW + 2, XF_IH = XF_TH + 2;  // depthwise input window
 constexpr int XF_LW = XF_TW / 2 + 2, XF_LH = XF_TH / 2 + 2;   // low-res window of an up-sampled tile
 constexpr int XF_RAW_BYTES = XF_IH * XF_IW * 128;    // 23040: 32 float32 channels (or 2 x 32 float16) per pixel
 constexpr int XF_UP_BYTES = XF_LH * XF_LW * 128;     // 7680
+constexpr int XF_WE_BYTES = 9 * 9 * 128;             // 10368: 3 x 3 row/column classes x 9 taps x 32 float32 channels
 constexpr int XF_A_PLANE = 128 * 128;                // 128 rows x 64 fp16
 constexpr int XF_A_BYTES = 2 * XF_A_PLANE;
 constexpr int XF_RING = 4;
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(XF_THREADS, 1)
 conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1_hi,
                const __grid_constant__ CUtensorMap tm1_lo, const __grid_constant__ CUtensorMap tmB_hi,
                const __grid_constant__ CUtensorMap tmB_lo, const __grid_constant__ CUtensorMap tmO_hi,
-               const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ XfK p) {
+               const __grid_constant__ CUtensorMap tmO_lo, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ XfK p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t raw_full[XF_RING], raw_empty[XF_RING], a_raw[XF_RING], a_full[XF_RING], a_empty[XF_RING],
         b_full[XF_RING], b_empty[XF_RING], tfull_bar[2], tempty_bar[2];
@@ -151,8 +153,11 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                             const uint32_t fb = smem_u32(&raw_full[st]);
                             const uint32_t dst = r_off + (uint32_t)st * XF_RAW_BYTES;
                             if (sm == XS_UP_F32) {
-                                mbar_expect_tx(fb, XF_UP_BYTES);
+                                // low-res window + the 3 x 3 block of row/column-class stencil weights this tile can need
+                                // (classes first|even|odd|last: a tile at the top/left border starts at "first", else at "even")
+                                mbar_expect_tx(fb, XF_UP_BYTES + XF_WE_BYTES);
                                 tma_load_4d(dst, &tm0, fb, c, (ox0 >> 1) - 1, (oy0 >> 1) - 1, img);
+                                tma_load_5d(dst + XF_UP_BYTES, &tmW, fb, 0, 0, ox0 == 0 ? 0 : 1, oy0 == 0 ? 0 : 1, c >> 5);
                             } else if (sm == XS_DW_F32) {
                                 mbar_expect_tx(fb, XF_RAW_BYTES);
                                 tma_load_4d(dst, &tm0, fb, c, ox0 - 1, oy0 - 1, img);
@@ -296,40 +301,36 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                         mbar_wait_g(smem_u32(&raw_full[rst]), rph);
                         const uint8_t* raw = smem_raw + (r_off + (uint32_t)rst * XF_RAW_BYTES - smem_u32(smem_raw));
                         if (sm == XS_UP_F32) {
-                            // bilinear x2 (half_pixel, edge-clamped) of the low-res window, evaluated in registers row by row:
-                            // U[2m] = .25 L[m-1] + .75 L[m], U[2m+1] = .75 L[m] + .25 L[m+1]; zero outside the map = conv padding
+                            // depthwise3x3(bilinear_x2(low)) == a 3x3 stencil on the LOW-res window whose weights depend only on
+                            // the output pixel's row/column class (plan.upcat_effective_weights): 9 FMAs per output, no
+                            // interpolation pass.  Interior warps read one weight per tap for all four pixel groups (broadcast).
                             const int ly0 = (oy0 >> 1) - 1, lx0 = (ox0 >> 1) - 1, c2 = ox >> 1;
-                            int lc[4];
+                            const int cy = oy == 0 ? 0 : (oy == p.H - 1 ? 3 : 1 + (oy & 1));
+                            const int cyl = cy - (oy0 == 0 ? 0 : 1), cx0 = ox0 == 0 ? 0 : 1;
+                            int lr[3], lc[4];
+                            const float* wq[4];
+                            const float* wt = reinterpret_cast<const float*>(raw + XF_UP_BYTES) + cl * 4;
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) lr[u] = min(max((oy >> 1) + u - 1, 0), p.Hl - 1) - ly0;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) lc[u] = min(max(c2 - 1 + u, 0), p.Wl - 1) - lx0;
-                            const bool left0 = ox == 0, right0 = ox + 4 >= p.W;
 #pragma unroll
-                            for (int jy = 0; jy < 3; ++jy) {
-                                const int uy = oy - 1 + jy;
-                                if (uy < 0 || uy >= p.H) continue;            // warp-uniform (one tile row per warp)
-                                const int m = uy >> 1, odd = uy & 1;
-                                const int ra = min(max(odd ? m : m - 1, 0), p.Hl - 1) - ly0;
-                                const int rb = min(max(odd ? m + 1 : m, 0), p.Hl - 1) - ly0;
-                                const float wa = odd ? 0.75f : 0.25f, wb = 1.f - wa;
-                                float4 V[4];
+                            for (int q = 0; q < 4; ++q) {
+                                const int x = ox + q;
+                                const int cx = x == 0 ? 0 : (x == p.W - 1 ? 3 : 1 + (x & 1));
+                                wq[q] = wt + ((cyl * 3 + (cx - cx0)) * 9) * 32;
+                            }
 #pragma unroll
-                                for (int u = 0; u < 4; ++u) {
-                                    const float4 la = *reinterpret_cast<const float4*>(raw + ((ra * XF_LW + lc[u]) * 32 + cl * 4) * 4);
-                                    const float4 lb = *reinterpret_cast<const float4*>(raw + ((rb * XF_LW + lc[u]) * 32 + cl * 4) * 4);
-                                    V[u] = f4_mix(wa, la, wb, lb);
-                                }
-                                float4 U[6];
-                                U[0] = f4_mix(0.75f, V[0], 0.25f, V[1]); U[1] = f4_mix(0.25f, V[0], 0.75f, V[1]);
-                                U[2] = f4_mix(0.75f, V[1], 0.25f, V[2]); U[3] = f4_mix(0.25f, V[1], 0.75f, V[2]);
-                                U[4] = f4_mix(0.75f, V[2], 0.25f, V[3]); U[5] = f4_mix(0.25f, V[2], 0.75f, V[3]);
-                                if (left0) U[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (right0) U[5] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int u = 0; u < 3; ++u) {
+                                float4 L[4];
 #pragma unroll
-                                for (int kx = 0; kx < 3; ++kx) {
-                                    const float4 w = *reinterpret_cast<const float4*>(dws + (jy * 3 + kx) * Kpad + cw);
+                                for (int v = 0; v < 4; ++v)
+                                    L[v] = *reinterpret_cast<const float4*>(raw + ((lr[u] * XF_LW + lc[v]) * 32 + cl * 4) * 4);
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) acc[q] = f4_fma(U[q + kx], w, acc[q]);
-                                }
+                                for (int v = 0; v < 3; ++v)
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        acc[q] = f4_fma(L[(q >> 1) + v], *reinterpret_cast<const float4*>(wq[q] + (u * 3 + v) * 32), acc[q]);
                             }
                         } else {
 #pragma unroll
@@ -543,7 +544,7 @@ bool xf_supported(const XfSetup& s) {
     if (s.x.H != s.out.H || s.x.W != s.out.W) return false;
     int K = s.x.C;
     if (s.low.base) {
-        if (!view_ok8(s.low) || s.low.fmt != DT_F32 || s.x.fmt != DT_SPLIT16) return false;    // one float32 source map per layer
+        if (!view_ok8(s.low) || s.low.fmt != DT_F32 || s.x.fmt != DT_SPLIT16 || !s.weff) return false;   // one float32 source map per layer
         if (s.low.C % 64 || s.out.H != 2 * s.low.H || s.out.W != 2 * s.low.W) return false;
         if (s.out.H % XF_TH || s.out.W % XF_TW) return false;
         K += s.low.C;
@@ -620,6 +621,18 @@ int xf_prepare(XfLayer& L, const XfSetup& s) {
             L.src1_hi = L.src0; L.src1_lo = L.src0;
         }
     }
+    L.w_eff = L.src0;
+    if (s.low.base) {
+        // [sub][cy 4][cx 4][tap 9][32 ch] float32; a tile takes the 3 x 3 classes it can contain
+        cuuint64_t dims[5] = {32, 9, 4, 4, (cuuint64_t)(s.low.C / 32)};
+        cuuint64_t strides[4] = {128, 9 * 128, 4 * 9 * 128, 16 * 9 * 128};
+        cuuint32_t box[5] = {32, 9, 3, 3, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&L.w_eff, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.weff, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SKPS_CHECK(r == CUDA_SUCCESS, "conv_xf: cuTensorMapEncodeTiled(weff) failed: %d", (int)r);
+    }
     const int K_pad = k.cchunks * 64;
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)s.n_tile};
@@ -687,7 +700,7 @@ static int xf_launch_t(const XfLayer& L, const XfK& k, int grid, cudaStream_t st
         attr_set = true;
     }
     conv_xf_kernel<MODE, ACT, SPLIT><<<grid, XF_THREADS, L.smem_bytes, stream>>>(L.src0, L.src1_hi, L.src1_lo, L.b_hi, L.b_lo,
-                                                                                  L.o_hi, L.o_lo, k);
+                                                                                  L.o_hi, L.o_lo, L.w_eff, k);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -741,17 +754,18 @@ struct DevBuf {
 //   x_split: the kernel reads x as fp16 hi/lo planes (else float32; XF_SCALE always splits)
 //   dww: [9][Kpad] depthwise weights then [Kpad] bias, Kpad = ceil((Cl+Cx)/64)*64 (XF_DW)
 //   w_hi/w_lo: (n_tile, Kpad) float16 as packed by plan.pack_tc_weights; residual (N,H,W,Cout) float32 or null
+//   weff: [Cl/32][4][4][9][32] class weights of the up-sampled channels (plan.pack_upcat_class_weights), null without low
 extern "C" SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int H, int W, int Cx, int x_split,
                                            const float* low, int Cl, const float* gate, const float* dww, int dw_act,
                                            const void* w_hi, const void* w_lo, const float* bias, int Cout, int act,
                                            int n_tile, float out_scale, const float* residual, int res_first,
-                                           int out_split, float* out) {
+                                           int out_split, float* out, const float* weff) {
     SKPS_CHECK(x && w_hi && w_lo && out && N > 0, "debug_conv_xf: null argument");
     const int K = Cx + (low ? Cl : 0), Kpad = (K + 63) / 64 * 64;
     const long long nx = (long long)N * H * W * Cx, nl = low ? (long long)N * (H / 2) * (W / 2) * Cl : 0;
     const long long nout = (long long)N * H * W * Cout;
     const bool xs = x_split || mode == XF_SCALE;
-    DevBuf dx, dxs, dl, dg, dw, dwh, dwl, db, dr, dout;
+    DevBuf dx, dxs, dl, dg, dw, dwh, dwl, db, dr, dout, dwe;
     SKPS_CHECK(!dx.alloc(nx * 4) && !dxs.alloc(nx * 4) && !dl.alloc(nl * 4) && !dg.alloc((size_t)N * Cx * 4) &&
                !dw.alloc((size_t)10 * Kpad * 4) && !dwh.alloc((size_t)n_tile * Kpad * 2) && !dwl.alloc((size_t)n_tile * Kpad * 2) &&
                !db.alloc((size_t)Cout * 4) && !dr.alloc(nout * 4) && !dout.alloc(nout * 4), "debug_conv_xf: cudaMalloc failed");
@@ -761,6 +775,10 @@ extern "C" SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int 
         SKPS_CUDA(cudaGetLastError());
     }
     if (low) SKPS_CUDA(cudaMemcpy(dl.p, low, nl * 4, cudaMemcpyHostToDevice));
+    if (low) {
+        SKPS_CHECK(weff && Cl % 32 == 0 && !dwe.alloc((size_t)Cl * 144 * 4), "debug_conv_xf: class weights");
+        SKPS_CUDA(cudaMemcpy(dwe.p, weff, (size_t)Cl * 144 * 4, cudaMemcpyHostToDevice));
+    }
     if (gate) SKPS_CUDA(cudaMemcpy(dg.p, gate, (size_t)N * Cx * 4, cudaMemcpyHostToDevice));
     if (dww) SKPS_CUDA(cudaMemcpy(dw.p, dww, (size_t)10 * Kpad * 4, cudaMemcpyHostToDevice));
     SKPS_CUDA(cudaMemcpy(dwh.p, w_hi, (size_t)n_tile * Kpad * 2, cudaMemcpyHostToDevice));
@@ -780,7 +798,7 @@ extern "C" SKPS_API int skps_debug_conv_xf(int mode, const float* x, int N, int 
     s.x = xs ? view(dxs.p, Cx, H, W, DT_SPLIT16, nx) : view(dx.p, Cx, H, W, DT_F32, 0);
     if (low) s.low = view(dl.p, Cl, H / 2, W / 2, DT_F32, 0);
     if (gate) s.gate = view(dg.p, Cx, 1, 1, DT_F32, 0);
-    s.dww = (const float*)dw.p; s.dw_act = dw_act;
+    s.dww = (const float*)dw.p; s.dw_act = dw_act; s.weff = low ? (const float*)dwe.p : nullptr;
     s.Cout = Cout; s.act = act; s.n_tile = n_tile; s.n_tiles = 1; s.out_scale = out_scale;
     s.w_hi = dwh.p; s.w_lo = dwl.p; s.bias = bias ? (const float*)db.p : nullptr;
     s.out = view(dout.p, Cout, H, W, out_split ? DT_SPLIT16 : DT_F32, nout);

@@ -36,7 +36,7 @@ struct XfK {
 };
 
 struct XfLayer {
-    CUtensorMap src0, src1_hi, src1_lo, b_hi, b_lo, o_hi, o_lo;
+    CUtensorMap src0, src1_hi, src1_lo, b_hi, b_lo, o_hi, o_lo, w_eff;
     XfK k;
     int mode, smem_bytes;
     bool valid = false;
@@ -49,6 +49,7 @@ struct XfSetup {
     // XF_DW:    x = depthwise input (F32 or SPLIT16), or the skip tensor when `low` is set; low = F32 low-res tensor (H/2 x W/2)
     TView x, low, gate;
     const float* dww;              // device: [9][Kpad] + [Kpad]
+    const float* weff;             // device: [low.C/32][4][4][9][32] row/column-class stencil weights of the up-sampled channels
     int dw_act;
     // pointwise conv
     int Cout, act, n_tile, n_tiles;

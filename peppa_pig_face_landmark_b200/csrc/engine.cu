@@ -309,6 +309,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
             s.low = resolve(e, op.in[2]);
             s.dww = e->d_weights + op.i[3];
             s.dw_act = (int)op.f[1];
+            s.weff = s.low.base ? e->d_weights + op.i2[0] : nullptr;
         } else {
             s.gate = resolve(e, op.in[2]);
         }

@@ -249,16 +249,16 @@ __device__ __forceinline__ float iou_track(const float* r1, const float* r2) {
     return inter / (sum - inter);
 }
 
-__global__ void __launch_bounds__(256) select_faces_kernel(const float* __restrict__ det, const int* __restrict__ det_count,
-                                                           int det_stride, const float* __restrict__ track, int n_track,
-                                                           float iou_thres, float alpha, float oma, float min_face,
-                                                           int top_k, float* __restrict__ boxes4, int* __restrict__ count) {
+__device__ __forceinline__ void select_faces_body(const float* __restrict__ det, int n_det, int det_stride,
+                                                  const float* __restrict__ track, int n_track, float iou_thres, float alpha,
+                                                  float oma, float min_face, int top_k, float* __restrict__ boxes4,
+                                                  int* __restrict__ count) {
     __shared__ float s_box[256][4];
     __shared__ float s_area[256];
     __shared__ int s_sel[256];
     __shared__ int s_m;
     const int tid = threadIdx.x;
-    const int n = min(*det_count, 256);
+    const int n = min(n_det, 256);
     if (tid < n) {
         const float* now = det + (long long)tid * det_stride;
         float b[4] = {now[0], now[1], now[2], now[3]};
@@ -301,6 +301,30 @@ __global__ void __launch_bounds__(256) select_faces_kernel(const float* __restri
     __syncthreads();
     const int m = s_m;
     if (tid < m * 4) boxes4[tid] = s_box[s_sel[tid / 4]][tid % 4];
+}
+
+__global__ void __launch_bounds__(256) select_faces_kernel(const float* __restrict__ det, const int* __restrict__ det_count,
+                                                           int det_stride, const float* __restrict__ track, int n_track,
+                                                           float iou_thres, float alpha, float oma, float min_face,
+                                                           int top_k, float* __restrict__ boxes4, int* __restrict__ count) {
+    select_faces_body(det, *det_count, det_stride, track, n_track, iou_thres, alpha, oma, min_face, top_k, boxes4, count);
+}
+
+// Multi-stream variant (mpipe.cu): block = stream.  flag[s] != 0: this frame ran the detector -> judge_boxs(track, det rows)
+// (facer.py:58); else boxes = the stream's track boxes (facer.py:61).  Track boxes and their count live on the device.
+__global__ void __launch_bounds__(256) mp_select_kernel(const float* __restrict__ det_rows, const int* __restrict__ det_count,
+                                                        int max_det, const int* __restrict__ flag,
+                                                        const float* __restrict__ track, const int* __restrict__ n_track,
+                                                        float iou_thres, float alpha, float oma, float min_face, int top_k,
+                                                        float* __restrict__ boxes4, int* __restrict__ count) {
+    const int s = blockIdx.x;
+    const float* trk = track + (long long)s * top_k * 4;
+    if (flag[s])
+        select_faces_body(det_rows + (long long)s * max_det * 16, det_count[s], 16, trk, n_track[s], iou_thres, alpha, oma,
+                          min_face, top_k, boxes4 + (long long)s * top_k * 4, count + s);
+    else
+        select_faces_body(trk, n_track[s], 4, nullptr, 0, iou_thres, alpha, oma, min_face, top_k,
+                          boxes4 + (long long)s * top_k * 4, count + s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -352,6 +376,15 @@ __global__ void __launch_bounds__(256) absdiff_sum_kernel(const uint8_t* __restr
         for (int w = 0; w < 8; ++w) t += warp_sum[w];
         atomicAdd(sum, t);
     }
+}
+
+int launch_mp_select(const float* det_rows, const int* det_count, int max_det, const int* flag, const float* track,
+                     const int* n_track, float iou_thres, float alpha, float oma, float min_face, int top_k, float* boxes4,
+                     int* count, int n_streams, cudaStream_t s) {
+    mp_select_kernel<<<n_streams, 256, 0, s>>>(det_rows, det_count, max_det, flag, track, n_track, iou_thres, alpha, oma,
+                                                min_face, top_k, boxes4, count);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace skps

@@ -965,6 +965,8 @@ def _fuse_dw_pw(pl):
                  name=d.name + "+" + c.name.split("/")[-2] if "/" in c.name else d.name + "+pw")
         o.w2 = lo
         o.extra, o.extra_slot = dww, 3
+        if up:
+            o.extra2 = P.pack_upcat_class_weights(d.w[:, :low.C])
         o.w_ref, o.dw_w, o.dw_b, o.dw_act = c.w_ref, d.w, d.b, d.act
         out.buf.dtype = out.buf.dtype            # the output keeps the format its readers asked for
         pl.ops[pl.ops.index(c)] = o

@@ -91,6 +91,8 @@ class Op:
         self.w2 = None                       # FLAG_TC: lo-plane weight matrix; its blob offset goes to ints[2]
         self.extra = None                    # op-specific float32 table; its blob offset goes to ints[extra_slot]
         self.extra_slot = 0
+        self.extra2 = None                   # second float32 table; its blob offset goes to ints2[0]
+        self.ints2 = [0, 0]
 
     def __repr__(self):
         return "%s %s -> %s act=%d k=%s s=%s d=%s %s" % (OP_NAMES[self.type], self.ins, self.outs,
@@ -164,6 +166,8 @@ class Plan:
                 ints = list(op.ints) + [0] * (4 - len(op.ints))
                 ints[op.extra_slot] = put(op.extra)
                 op.ints = ints
+            if op.extra2 is not None:
+                op.ints2 = [put(op.extra2), 0]
         # tail slack: kernels that read weight rows in whole 16-byte / 64-channel pieces never run past the allocation
         parts.append(np.zeros(256, np.float32))
         return np.concatenate(parts)
@@ -187,6 +191,7 @@ class Plan:
             fl = np.asarray(list(op.floats) + [0.0] * (8 - len(op.floats)), np.float32)[:8]
             w += fl.view(np.int32).tolist()
             w += op.ins[3].words() if len(op.ins) > 3 and op.ins[3] is not None else _NOVIEW     # 4th input (OP_ADDN)
+            w += list(op.ints2)
             assert len(w) <= OP_WORDS, len(w)
             w += [0] * (OP_WORDS - len(w))
             ow += w
@@ -303,6 +308,16 @@ def upcat_effective_weights(w9c):
         for cx in range(4):
             out[cy, cx] = np.einsum("ykc,ya,kb->abc", w, R[cy], R[cx])
     return np.ascontiguousarray(out.astype(np.float32))
+
+
+def pack_upcat_class_weights(w9c):
+    """upcat_effective_weights() re-laid for csrc/conv_xf.cu: [C/32][cy 4][cx 4][tap 9][32] float32, so that one 5-D TMA box
+    (32 ch, 9 taps, 3 column classes, 3 row classes) fetches what one output tile of a 32-channel sub-chunk needs."""
+    e = upcat_effective_weights(w9c)                       # [4][4][3][3][C]
+    C = e.shape[-1]
+    assert C % 32 == 0
+    e = e.reshape(4, 4, 9, C // 32, 32).transpose(3, 0, 1, 2, 4)
+    return np.ascontiguousarray(e, dtype=np.float32)
 
 
 def pack_mma_weights(w_ockk):

@@ -41,12 +41,13 @@ def _run(mode, N, H, W, Cx, Cout, Cl=0, x_split=False, dw_act=0, act=0, with_res
     hi, lo, out_scale = P.pack_tc_weights(w, n_tile, n_tiles)
     hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
     out = np.full((N, H, W, Cout), np.nan, np.float32)
+    weff = P.pack_upcat_class_weights(dw_w[:, :Cl]) if Cl else None
     rt.check(lib.skps_debug_conv_xf(mode, x.ctypes.data, N, H, W, Cx, 1 if x_split else 0,
                                     low.ctypes.data if low is not None else None, Cl,
                                     gate.ctypes.data if gate is not None else None, dww.ctypes.data, dw_act,
                                     hi.ctypes.data, lo.ctypes.data, b.ctypes.data, Cout, act, n_tile, out_scale,
                                     res.ctypes.data if res is not None else None, 0, 1 if out_split else 0,
-                                    out.ctypes.data))
+                                    out.ctypes.data, weff.ctypes.data if weff is not None else None))
     xt = torch.from_numpy(x).permute(0, 3, 1, 2)
     if mode == 0:
         a = xt * torch.from_numpy(gate)[:, :, None, None]

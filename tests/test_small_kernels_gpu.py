@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 def _select(lib, rt, torch, det, track, top_k, min_face=1600.0, iou=0.5, alpha=0.3):
     n = det.shape[0]
-    d_det = torch.from_numpy(np.ascontiguousarray(det, np.float32)).cuda()
+    d_det = torch.from_numpy(np.ascontiguousarray(det if n else np.zeros((1, det.shape[1])), np.float32)).cuda()   # non-null when empty
     d_cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
     d_trk = torch.from_numpy(np.ascontiguousarray(track, np.float32)).cuda() if track is not None and len(track) else None
     d_box = torch.zeros((top_k, 4), dtype=torch.float32, device="cuda")
@@ -43,7 +43,7 @@ def test_select_faces_matches_oracle(seed, n, n_track, top_k):
             rng.uniform(0, 500, (n_track, 4)).astype(np.float32)
     got = _select(lib, rt, torch, det, track, top_k)
     want = host_ref.sort_and_filter(host_ref.judge_boxs(track, det) if n else np.zeros((0, 4), np.float32), 1600, top_k)
-    want = np.asarray(want, np.float64).reshape(-1, 4)
+    want = np.asarray(want, np.float64).reshape(-1, det.shape[1] if (n and track is None) else 4)[:, :4]
     assert got.shape == want.shape, (got.shape, want.shape)
     assert np.abs(got - want).max(initial=0) <= 1e-3          # EMA in float32 on the device, float64 mix on the host
 

@@ -5,7 +5,7 @@ set +e
 OUT=gpurun_out/$1
 mkdir -p $OUT
 echo "== unit tests" | tee $OUT/steps.log
-timeout 300 python -m pytest tests/test_conv_xf_gpu.py tests/test_small_kernels_gpu.py -q -x > $OUT/t_unit.log 2>&1; echo "unit rc=$?" | tee -a $OUT/steps.log
+timeout 300 python -m pytest tests/test_conv_xf_gpu.py -q -x -s > $OUT/t_unit.log 2>&1; echo "unit rc=$?" | tee -a $OUT/steps.log
 tail -4 $OUT/t_unit.log
 if grep -q "unit rc=[^0]" $OUT/steps.log; then grep -E "^E  |rel err" $OUT/t_unit.log | head -20; exit 0; fi
 echo "== gpu suite" | tee -a $OUT/steps.log
