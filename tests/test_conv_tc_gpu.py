@@ -136,3 +136,35 @@ def test_conv_mma_small_channel_3x3():
     assert _run_mma(3, 32, 32, 40, 1, with_res=True, res_first=True, out_split=False) < 1e-5
     assert _run_mma(2, 32, 32, 40, 0, with_res=True, res_first=False) < 1e-5
     assert _run_mma(1, 24, 40, 24, 0) < 1e-5                                             # partial tiles in both directions
+
+
+@pytest.mark.parametrize("x_scale", [1e-3, 1.0, 1e3])
+def test_conv_tc_elementwise_error_bound_small_and_large_inputs(x_scale):
+    """Range check of the fp16 hi/lo operand format: inputs of magnitude 1e-3 .. 1e+3, and an
+    ELEMENT-wise bound instead of a max-norm one: |out - ref| <= 2^-19 * sum_k |x_k| |w_k| + tiny, the backward-error
+    form of a dot product evaluated with ~2^-22 operand error and fp32 accumulation.  For |x| ~ 1e-3 the lo plane falls
+    into float16's subnormal range (absolute error 2^-25 per operand), which this bound still has to hold."""
+    import torch
+    import torch.nn.functional as F
+    from peppa_pig_face_landmark_b200 import plan as P, runtime as rt
+    lib = rt.load_library()
+    rng = np.random.default_rng(17)
+    N, H, W, Cin, Cout, k = 2, 32, 32, 120, 40, 3
+    x = (rng.standard_normal((N, H, W, Cin)) * x_scale).astype(np.float32)
+    x[0, :4] *= 1e-2                                      # a region two more decades down
+    w = (rng.standard_normal((Cout, k, k, Cin)) / np.sqrt(k * k * Cin)).astype(np.float32)
+    n_tile, n_tiles = P.tc_tiling(Cout)
+    hi, lo, out_scale = P.pack_tc_weights(w, n_tile, n_tiles)
+    hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
+    out = np.empty((N, H, W, Cout), np.float32)
+    rt.check(lib.skps_debug_conv_tc2(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data, None, Cout, k, 1, 0,
+                                     n_tile, n_tiles, out_scale, None, 0, out.ctypes.data, 1, 0, N))
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2).double()
+    wt = torch.from_numpy(w).permute(0, 3, 1, 2).contiguous().double()
+    ref = F.conv2d(xt, wt, padding=1).permute(0, 2, 3, 1).numpy()
+    mag = F.conv2d(xt.abs(), wt.abs(), padding=1).permute(0, 2, 3, 1).numpy()
+    err = np.abs(out - ref)
+    bound = 2.0 ** -19 * mag + 1e-9 * x_scale
+    worst = (err / bound).max()
+    print("conv_tc element-wise error / bound at |x|~%g: %.3f" % (x_scale, worst))
+    assert worst <= 1.0

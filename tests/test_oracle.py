@@ -108,3 +108,23 @@ def test_detector_graph_cross_check_cv2_dnn(ref_nets):
     mine = np.asarray(det.net.run(x)[0]).reshape(15120, 16)
     assert np.abs(y - mine).max() < 2e-3
     assert np.array_equal(np.where(y[:, 4] > 0.5)[0], np.where(mine[:, 4] > 0.5)[0])
+
+
+def test_student_executor_fp64_tie_breaker():
+    """kps_student.onnx has a single independent executor here (cv2.dnn cannot import it), so the same
+    executor run in float64 is the tie-breaker reference: the float32 oracle every parity test compares against must sit
+    within a small fraction of the 1e-3 px budget of the float64 result, arg-max decisions included."""
+    import torch
+    import frames
+    from oracle.onnx_exec import Session
+    from oracle.faceana_ref import LandmarkRef
+    import os
+    path = os.path.join(os.path.dirname(__file__), "..", "peppa_pig_face_landmark_b200", "pretrained", "kps_student.onnx")
+    crops = frames.crop_variants(3)
+    s64 = Session(path, dtype=torch.float64)
+    xy32, sc32 = LandmarkRef().forward_crops(crops)
+    for i, c in enumerate(crops):
+        o, k = s64.run(c.transpose(2, 0, 1)[None].astype(np.float64) / 255.0)
+        dpx = np.abs(np.asarray(o).reshape(98, 2) - np.asarray(xy32[i], np.float64)).max() * 256
+        dsc = np.abs(np.asarray(k).reshape(-1) - np.asarray(sc32[i], np.float64)).max()
+        assert dpx < 1e-4 and dsc < 1e-5, (i, dpx, dsc)
