@@ -35,7 +35,7 @@ constexpr int XF_IW = XF_TW + 2, XF_IH = XF_TH + 2;  // depthwise input window
 constexpr int XF_LW = XF_TW / 2 + 2, XF_LH = XF_TH / 2 + 2;   // low-res window of an up-sampled tile
 constexpr int XF_RAW_BYTES = XF_IH * XF_IW * 128;    // 23040: 32 float32 channels (or 2 x 32 float16) per pixel
 constexpr int XF_UP_BYTES = XF_LH * XF_LW * 128;     // 7680
-constexpr int XF_WE_BYTES = 9 * 9 * 128;             // 10368: 3 x 3 row/column classes x 9 taps x 32 float32 channels
+// + stencil weights of the up-sampled channels: (3 row classes) x (3 or 4 column classes) x 9 taps x 32 float32 channels
 constexpr int XF_A_PLANE = 128 * 128;                // 128 rows x 64 fp16
 constexpr int XF_A_BYTES = 2 * XF_A_PLANE;
 constexpr int XF_RING = 4;
@@ -155,9 +155,10 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                             if (sm == XS_UP_F32) {
                                 // low-res window + the 3 x 3 block of row/column-class stencil weights this tile can need
                                 // (classes first|even|odd|last: a tile at the top/left border starts at "first", else at "even")
-                                mbar_expect_tx(fb, XF_UP_BYTES + XF_WE_BYTES);
+                                // (a map one tile wide holds first AND last columns: 4 column classes, p.wcx = 4)
+                                mbar_expect_tx(fb, XF_UP_BYTES + (uint32_t)p.wcx * 3u * 9u * 128u);
                                 tma_load_4d(dst, &tm0, fb, c, (ox0 >> 1) - 1, (oy0 >> 1) - 1, img);
-                                tma_load_5d(dst + XF_UP_BYTES, &tmW, fb, 0, 0, ox0 == 0 ? 0 : 1, oy0 == 0 ? 0 : 1, c >> 5);
+                                tma_load_5d(dst + XF_UP_BYTES, &tmW, fb, 0, 0, (p.wcx == 4 || ox0 == 0) ? 0 : 1, oy0 == 0 ? 0 : 1, c >> 5);
                             } else if (sm == XS_DW_F32) {
                                 mbar_expect_tx(fb, XF_RAW_BYTES);
                                 tma_load_4d(dst, &tm0, fb, c, ox0 - 1, oy0 - 1, img);
@@ -306,7 +307,7 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                             // interpolation pass.  Interior warps read one weight per tap for all four pixel groups (broadcast).
                             const int ly0 = (oy0 >> 1) - 1, lx0 = (ox0 >> 1) - 1, c2 = ox >> 1;
                             const int cy = oy == 0 ? 0 : (oy == p.H - 1 ? 3 : 1 + (oy & 1));
-                            const int cyl = cy - (oy0 == 0 ? 0 : 1), cx0 = ox0 == 0 ? 0 : 1;
+                            const int cyl = cy - (oy0 == 0 ? 0 : 1), cx0 = (p.wcx == 4 || ox0 == 0) ? 0 : 1;
                             int lr[3], lc[4];
                             const float* wq[4];
                             const float* wt = reinterpret_cast<const float*>(raw + XF_UP_BYTES) + cl * 4;
@@ -318,7 +319,7 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                             for (int q = 0; q < 4; ++q) {
                                 const int x = ox + q;
                                 const int cx = x == 0 ? 0 : (x == p.W - 1 ? 3 : 1 + (x & 1));
-                                wq[q] = wt + ((cyl * 3 + (cx - cx0)) * 9) * 32;
+                                wq[q] = wt + ((cyl * p.wcx + (cx - cx0)) * 9) * 32;
                             }
 #pragma unroll
                             for (int u = 0; u < 3; ++u) {
@@ -546,7 +547,7 @@ bool xf_supported(const XfSetup& s) {
     if (s.low.base) {
         if (!view_ok8(s.low) || s.low.fmt != DT_F32 || s.x.fmt != DT_SPLIT16 || !s.weff) return false;   // one float32 source map per layer
         if (s.low.C % 64 || s.out.H != 2 * s.low.H || s.out.W != 2 * s.low.W) return false;
-        if (s.out.H % XF_TH || s.out.W % XF_TW) return false;
+        if (s.out.H % XF_TH || s.out.W % XF_TW || s.out.H < 2 * XF_TH) return false;     // no tile holds first AND last rows
         K += s.low.C;
     }
     return (K + 63) / 64 <= XF_MAX_CHUNKS;
@@ -626,7 +627,8 @@ int xf_prepare(XfLayer& L, const XfSetup& s) {
         // [sub][cy 4][cx 4][tap 9][32 ch] float32; a tile takes the 3 x 3 classes it can contain
         cuuint64_t dims[5] = {32, 9, 4, 4, (cuuint64_t)(s.low.C / 32)};
         cuuint64_t strides[4] = {128, 9 * 128, 4 * 9 * 128, 16 * 9 * 128};
-        cuuint32_t box[5] = {32, 9, 3, 3, 1};
+        k.wcx = k.tiles_x == 1 ? 4 : 3;
+        cuuint32_t box[5] = {32, 9, (cuuint32_t)k.wcx, 3, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&L.w_eff, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.weff, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

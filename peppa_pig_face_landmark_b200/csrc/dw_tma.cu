@@ -96,15 +96,24 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
     const int row0 = RY == 1 ? pr : (pr / D) * (RY * D) + (pr % D);
     const int c = chunk * CB + cg * 4;
     const bool c_ok = c < p.C;
+    // this CTA's slice of the weights ([K*K][CB]) and bias, staged in shared memory while the TMA load is in flight: the
+    // tap loop reads them as warp-wide broadcasts instead of one global load per tap (ncu r1: long-scoreboard stalls on them)
+    __shared__ float4 wsm[K * K + 1][CG];
+    for (int i = tid; i < (K * K + 1) * CG; i += DW_THREADS) {
+        const int r = i / CG, g = i - r * CG, cc = chunk * CB + g * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc < p.C) v = *reinterpret_cast<const float4*>((r < K * K ? p.w + (long long)r * p.w_ld : p.bias) + cc);
+        wsm[r][g] = v;
+    }
+    __syncthreads();        // weights staged; barrier init visible to all waiters
     float4 acc[RY][PX];
     {
-        const float4 b = c_ok ? *reinterpret_cast<const float4*>(p.bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b = wsm[K * K][cg];
 #pragma unroll
         for (int ry = 0; ry < RY; ++ry)
 #pragma unroll
             for (int q = 0; q < PX; ++q) acc[ry][q] = b;
     }
-    __syncthreads();        // barrier init visible to all waiters
     {
         asm volatile(
             "{\n\t"
@@ -150,7 +159,7 @@ dw_tma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__
             for (int kx = 0; kx < K; ++kx) {
                 float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < K) {
-                    w = *reinterpret_cast<const float4*>(p.w + (j * K + kx) * p.w_ld + c);
+                    w = wsm[j * K + kx][cg];
 #pragma unroll
                     for (int q = 0; q < PX; ++q) {
                         const float4 v = in[q * S + kx * D];

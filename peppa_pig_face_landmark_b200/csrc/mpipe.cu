@@ -250,7 +250,10 @@ extern "C" SKPS_API int skps_mpipe_submit(skps_mpipe* p, int slot_i, const uint8
     a.state_idx = p->d_state_idx; a.track_box = p->d_track; a.track_f32 = p->d_track_f32; a.n_track = p->d_n_track;
     a.out_kps = p->d_out_kps;
     // the python floats of lk.py / facer.py, evaluated in the same order
-    a.iou_thres = (double)c.track_iou; a.alpha = (double)c.alpha; a.one_minus_alpha = 1.0 - (double)c.alpha;
+    // (the cfg carries them as float32; Skps.yml's 0.5 / 0.3 come back exactly by rounding to 6 decimals in double)
+    a.iou_thres = nearbyint((double)c.track_iou * 1e6) / 1e6;
+    a.alpha = nearbyint((double)c.alpha * 1e6) / 1e6;
+    a.one_minus_alpha = 1.0 - a.alpha;
     a.two_pi = 2 * 3.141592653589793;
     { const double r = a.two_pi * 1.0 * 1.0; a.a_d = r / (r + 1); a.one_minus_a_d = 1 - a.a_d; }
     a.min_cutoff = 0.15; a.beta = 0.8;

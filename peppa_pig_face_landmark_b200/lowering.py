@@ -943,7 +943,7 @@ def _fuse_dw_pw(pl):
         if not ok8(x) or x.buf.dtype not in (P.DT_F32, P.DT_SPLIT16) or out.H < 8 or out.W < 16:
             continue
         if up and (not ok8(low) or low.buf.dtype != P.DT_F32 or x.buf.dtype != P.DT_SPLIT16 or low.C % 64
-                   or out.H % 8 or out.W % 16):
+                   or out.H % 8 or out.W % 16 or out.H < 16):
             continue
         K = x.C + (low.C if up else 0)
         n_tile, n_tiles = P.tc_tiling(out.C)
