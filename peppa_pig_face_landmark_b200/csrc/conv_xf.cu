@@ -98,7 +98,7 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < XF_RING; ++s) {
             mbar_init(smem_u32(&raw_full[s]), 1);
-            mbar_init(smem_u32(&raw_empty[s]), 8);           // one arrival per transform warp
+            mbar_init(smem_u32(&raw_empty[s]), 4);           // one arrival per warp of the half that consumes the slot
             mbar_init(smem_u32(&a_raw[s]), 1);
             mbar_init(smem_u32(&a_full[s]), 8);
             mbar_init(smem_u32(&a_empty[s]), 1);
@@ -283,63 +283,99 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                 }
             }
         } else {
-            // thread = 4 consecutive output pixels of one tile row x 4 channels of the 32-channel sub-chunk
-            const int cl = tt & 7, pg = tt >> 3, prow = pg >> 2, xs = (pg & 3) * 4;
+            // The 256 transform threads split into two halves, one per 32-channel sub-chunk of the current 64-channel chunk.
+            // A thread = 4 channels x a 2-row x 4-pixel patch of the tile: every staged value it loads feeds several outputs
+            // (the first version - one row per thread - was shared-memory-bandwidth bound: l1tex 80 %, 12 LDS.128 per output).
+            //   depthwise 3x3      rows (2k, 2k+1): 4 window rows x 6 columns + 9 weights           = 33 loads / 8 outputs
+            //   up-sampled stencil rows (r, r+2) of equal parity share their class weights:
+            //                      4 low-res rows x 4 columns + 2 column classes x 9 taps             = 34 loads / 8 outputs
+            const int half = tt >> 7, t7 = tt & 127;
+            const int cl = t7 & 7, pg = t7 >> 3, xs = (pg & 3) * 4, rp = pg >> 2;
             const float* dws = reinterpret_cast<const float*>(smem_raw + (w_off - smem_u32(smem_raw)));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int t = tile % p.tiles_per_img;
                 const int oy0 = (t / p.tiles_x) * XF_TH, ox0 = (t % p.tiles_x) * XF_TW;
-                const int oy = oy0 + prow, ox = ox0 + xs;
+                const int ox = ox0 + xs;
                 for (int kc = 0; kc < p.cchunks; ++kc) {
                     mbar_wait_g(smem_u32(&a_empty[ast]), aph ^ 1u);
                     const uint32_t sa = a_off + (uint32_t)ast * XF_A_BYTES;
                     const int subs = p.chunk_subs[kc];
-                    for (int h = 0; h < subs; ++h) {
-                        const int sm = p.sub_mode[kc * 2 + h];
-                        const int cw = kc * 64 + h * 32 + cl * 4;
+                    if (half < subs) {
+                        // ring slot of this half's sub-chunk: sub 0 sits at rst, sub 1 one slot further
+                        int slot = rst + half;
+                        uint32_t sph = rph;
+                        if (slot >= p.rs) { slot -= p.rs; sph ^= 1u; }
+                        const int sm = p.sub_mode[kc * 2 + half];
+                        const int cw = kc * 64 + half * 32 + cl * 4;
                         const float4 bias4 = *reinterpret_cast<const float4*>(dws + 9 * Kpad + cw);
-                        float4 acc[4] = {bias4, bias4, bias4, bias4};
-                        mbar_wait_g(smem_u32(&raw_full[rst]), rph);
-                        const uint8_t* raw = smem_raw + (r_off + (uint32_t)rst * XF_RAW_BYTES - smem_u32(smem_raw));
+                        float4 acc[2][4] = {{bias4, bias4, bias4, bias4}, {bias4, bias4, bias4, bias4}};
+                        int r0, r1;                                       // the two tile rows of this thread
+                        mbar_wait_g(smem_u32(&raw_full[slot]), sph);
+                        const uint8_t* raw = smem_raw + (r_off + (uint32_t)slot * XF_RAW_BYTES - smem_u32(smem_raw));
                         if (sm == XS_UP_F32) {
                             // depthwise3x3(bilinear_x2(low)) == a 3x3 stencil on the LOW-res window whose weights depend only on
-                            // the output pixel's row/column class (plan.upcat_effective_weights): 9 FMAs per output, no
-                            // interpolation pass.  Interior warps read one weight per tap for all four pixel groups (broadcast).
-                            const int ly0 = (oy0 >> 1) - 1, lx0 = (ox0 >> 1) - 1, c2 = ox >> 1;
-                            const int cy = oy == 0 ? 0 : (oy == p.H - 1 ? 3 : 1 + (oy & 1));
-                            const int cyl = cy - (oy0 == 0 ? 0 : 1), cx0 = (p.wcx == 4 || ox0 == 0) ? 0 : 1;
-                            int lr[3], lc[4];
-                            const float* wq[4];
+                            // the output pixel's row/column class first|even|odd|last (plan.upcat_effective_weights)
+                            r0 = (rp >> 1) * 4 + (rp & 1); r1 = r0 + 2;
+                            const int y0 = oy0 + r0, y1 = oy0 + r1;
+                            const int ly0 = (oy0 >> 1) - 1, lx0 = (ox0 >> 1) - 1, m = y0 >> 1, c2 = ox >> 1;
+                            const int cyb = oy0 == 0 ? 0 : 1, cxb = (p.wcx == 4 || ox0 == 0) ? 0 : 1;
+                            const int cyA = (y0 == 0 ? 0 : (y0 == p.H - 1 ? 3 : 1 + (y0 & 1))) - cyb;
+                            const int cyB = (y1 == 0 ? 0 : (y1 == p.H - 1 ? 3 : 1 + (y1 & 1))) - cyb;
+                            const bool same_cy = cyA == cyB;                  // warp-uniform (one row pair per warp)
+                            const bool xfirst = ox == 0, xlast = ox + 4 == p.W;
                             const float* wt = reinterpret_cast<const float*>(raw + XF_UP_BYTES) + cl * 4;
+                            const int sE = (1 - cxb) * 9 * 32, sO = (2 - cxb) * 9 * 32, sF = 0, sL = (3 - cxb) * 9 * 32;
+                            const float* wA = wt + cyA * p.wcx * 9 * 32;
+                            const float* wB = wt + cyB * p.wcx * 9 * 32;
+                            int lr[4], lc[4];
 #pragma unroll
-                            for (int u = 0; u < 3; ++u) lr[u] = min(max((oy >> 1) + u - 1, 0), p.Hl - 1) - ly0;
+                            for (int u = 0; u < 4; ++u) lr[u] = min(max(m - 1 + u, 0), p.Hl - 1) - ly0;
 #pragma unroll
                             for (int u = 0; u < 4; ++u) lc[u] = min(max(c2 - 1 + u, 0), p.Wl - 1) - lx0;
+                            float4 wpE[3], wpO[3];                            // previous tap row's weights (row r1 lags one low row)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int x = ox + q;
-                                const int cx = x == 0 ? 0 : (x == p.W - 1 ? 3 : 1 + (x & 1));
-                                wq[q] = wt + ((cyl * p.wcx + (cx - cx0)) * 9) * 32;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 3; ++u) {
+                            for (int u = 0; u < 4; ++u) {
                                 float4 L[4];
 #pragma unroll
                                 for (int v = 0; v < 4; ++v)
                                     L[v] = *reinterpret_cast<const float4*>(raw + ((lr[u] * XF_LW + lc[v]) * 32 + cl * 4) * 4);
 #pragma unroll
-                                for (int v = 0; v < 3; ++v)
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q)
-                                        acc[q] = f4_fma(L[(q >> 1) + v], *reinterpret_cast<const float4*>(wq[q] + (u * 3 + v) * 32), acc[q]);
+                                for (int v = 0; v < 3; ++v) {
+                                    float4 wE = wpE[v], wO = wpO[v];          // (u - 1, v) weights of the shared class
+                                    if (u > 0) {                              // row r1: this low row is its tap row a = u - 1
+                                        const int o = ((u - 1) * 3 + v) * 32;
+                                        if (!same_cy) {
+                                            wE = *reinterpret_cast<const float4*>(wB + sE + o);
+                                            wO = *reinterpret_cast<const float4*>(wB + sO + o);
+                                        }
+                                        float4 x0 = wE, x3 = wO;
+                                        if (xfirst) x0 = *reinterpret_cast<const float4*>(wB + sF + o);
+                                        if (xlast) x3 = *reinterpret_cast<const float4*>(wB + sL + o);
+                                        acc[1][0] = f4_fma(L[v], x0, acc[1][0]); acc[1][1] = f4_fma(L[v], wO, acc[1][1]);
+                                        acc[1][2] = f4_fma(L[1 + v], wE, acc[1][2]); acc[1][3] = f4_fma(L[1 + v], x3, acc[1][3]);
+                                    }
+                                    if (u < 3) {                              // row r0: this low row is its tap row a = u
+                                        const int o = (u * 3 + v) * 32;
+                                        wE = *reinterpret_cast<const float4*>(wA + sE + o);
+                                        wO = *reinterpret_cast<const float4*>(wA + sO + o);
+                                        float4 x0 = wE, x3 = wO;
+                                        if (xfirst) x0 = *reinterpret_cast<const float4*>(wA + sF + o);
+                                        if (xlast) x3 = *reinterpret_cast<const float4*>(wA + sL + o);
+                                        acc[0][0] = f4_fma(L[v], x0, acc[0][0]); acc[0][1] = f4_fma(L[v], wO, acc[0][1]);
+                                        acc[0][2] = f4_fma(L[1 + v], wE, acc[0][2]); acc[0][3] = f4_fma(L[1 + v], x3, acc[0][3]);
+                                        wpE[v] = wE; wpO[v] = wO;
+                                    }
+                                }
                             }
                         } else {
+                            r0 = 2 * rp; r1 = r0 + 1;
+                            float4 wprev[3];
 #pragma unroll
-                            for (int ky = 0; ky < 3; ++ky) {
+                            for (int u = 0; u < 4; ++u) {                     // window row r0 + u: tap row u of r0, u - 1 of r1
                                 float4 in[6];
 #pragma unroll
                                 for (int i = 0; i < 6; ++i) {
-                                    const int px = (prow + ky) * XF_IW + xs + i;
+                                    const int px = (r0 + u) * XF_IW + xs + i;
                                     if (sm == XS_DW_F32) {
                                         in[i] = *reinterpret_cast<const float4*>(raw + (px * 32 + cl * 4) * 4);
                                     } else {
@@ -354,31 +390,42 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                                 }
 #pragma unroll
                                 for (int kx = 0; kx < 3; ++kx) {
-                                    const float4 w = *reinterpret_cast<const float4*>(dws + (ky * 3 + kx) * Kpad + cw);
+                                    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (u < 3) {
+                                        w = *reinterpret_cast<const float4*>(dws + (u * 3 + kx) * Kpad + cw);
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) acc[q] = f4_fma(in[q + kx], w, acc[q]);
+                                        for (int q = 0; q < 4; ++q) acc[0][q] = f4_fma(in[q + kx], w, acc[0][q]);
+                                    }
+                                    if (u > 0) {
+                                        const float4 x = wprev[kx];
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q) acc[1][q] = f4_fma(in[q + kx], x, acc[1][q]);
+                                    }
+                                    wprev[kx] = w;
                                 }
                             }
                         }
                         // the raw tile has been consumed into registers: hand the slot back to the TMA producer
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&raw_empty[rst]));
-                        if (++rst == p.rs) { rst = 0; rph ^= 1u; }
+                        if (lane == 0) mbar_arrive(smem_u32(&raw_empty[slot]));
                         // activation, fp16 hi/lo split, store into the swizzled K-major A tile
-                        const int jc = h * 4 + (cl >> 1);                    // logical 16-byte chunk of the 128-byte row
                         switch (p.dw_act) {               // one branch per sub-chunk, not one per element
-                            case ACT_RELU: act16<ACT_RELU>(acc); break;
-                            case ACT_HSWISH: act16<ACT_HSWISH>(acc); break;
-                            case ACT_SILU: act16<ACT_SILU>(acc); break;
+                            case ACT_RELU: act16<ACT_RELU>(acc[0]); act16<ACT_RELU>(acc[1]); break;
+                            case ACT_HSWISH: act16<ACT_HSWISH>(acc[0]); act16<ACT_HSWISH>(acc[1]); break;
+                            case ACT_SILU: act16<ACT_SILU>(acc[0]); act16<ACT_SILU>(acc[1]); break;
                             default: break;
                         }
+                        const int jc = half * 4 + (cl >> 1);                 // logical 16-byte chunk of the 128-byte row
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 v = acc[q];
-                            const int r = prow * XF_TW + xs + q;
-                            split_store4(sa + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4) + (uint32_t)(cl & 1) * 8u, v);
-                        }
+                        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int r = (rr ? r1 : r0) * XF_TW + xs + q;
+                                split_store4(sa + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4) + (uint32_t)(cl & 1) * 8u, acc[rr][q]);
+                            }
                     }
+                    rst += subs;
+                    if (rst >= p.rs) { rst -= p.rs; rph ^= 1u; }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&a_full[ast]));
@@ -676,9 +723,11 @@ int xf_prepare(XfLayer& L, const XfSetup& s) {
     auto total = [&]() { return (size_t)k.as * XF_A_BYTES + (size_t)k.bs * b_slot + (size_t)k.out_bufs * 16384 +
                                 (size_t)k.rs * XF_RAW_BYTES + w_bytes; };
     SKPS_CHECK(total() <= budget, "conv_xf: layer does not fit shared memory (%zu bytes)", total());
+    // two halves consume two raw slots at once: a third slot is what lets the TMA producer run ahead
     if (s.mode == XF_DW) { k.rs = 3; if (total() > budget) k.rs = 2; }
+    if (k.tma_store) { k.out_bufs = 2; if (total() > budget) k.out_bufs = 1; }     // the store of chunk i drains under chunk i+1
     k.bs = 3; if (total() > budget) k.bs = 2;
-    if (k.tma_store) { k.out_bufs = 2; if (total() > budget) k.out_bufs = 1; }
+    if (s.mode == XF_DW && k.rs == 3) { k.rs = 4; if (total() > budget) k.rs = 3; }
     k.as = 3; if (total() > budget) k.as = 2;
     if (k.bs == 3) { k.bs = 4; if (total() > budget) k.bs = 3; }
     L.smem_bytes = (int)(total() + 1024);
