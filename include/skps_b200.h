@@ -218,6 +218,22 @@ SKPS_API int skps_pipeline_frame_diff(skps_pipeline* p, const uint8_t* frame, in
  * FaceAna.run (facer.py:57-62 replaces previous_image on every call, also when nothing is detected or tracked). */
 SKPS_API int skps_pipeline_commit_frame(skps_pipeline* p, int H, int W);
 
+/* WFLW evaluation helpers (TRAIN/face_landmark/tools/eval_WFLW.py).  skps_crop_rect: zero-bordered rectangular crop of a
+ * [dev] BGR frame resized to out_hw x out_hw, bit-exact with copyMakeBorder + slicing + cv2.resize (:38-80, :113-124).
+ * skps_nme: per-face normalised mean error, mean_p |pred - gt| / |gt[norm_a] - gt[norm_b]| (:84-95; WFLW: 60, 72); all [dev]. */
+SKPS_API int skps_crop_rect(const uint8_t* frame, int H, int W, int pitch, int rx, int ry, int rw, int rh, uint8_t* out,
+                            int out_hw, void* stream);
+SKPS_API int skps_nme(const float* target, const float* preds, int n, int n_points, int norm_a, int norm_b, float* out,
+                      void* stream);
+
+/* Batched head pose (csrc/headpose.cu), the GPU counterpart of Skps/core/headpose/pose.py:48-77 get_head_pose():
+ * solvePnP (iterative) on 10 landmark/model point pairs with the camera matrix [[w,0,w//2],[0,w,h//2],[0,0,1]], projection
+ * of the 8 cube corners, Euler angles as cv2.decomposeProjectionMatrix reports them.  pts [host] (N,10,2) float32 in the
+ * order of pose.py:60-61; object_pts (10,3), cube_pts (8,3) float32.  Outputs [host] float64: rvec, tvec, euler (N,3),
+ * reproject (N,8,2). */
+SKPS_API int skps_head_pose(const float* pts, int N, int img_w, int img_h, const float* object_pts, const float* cube_pts,
+                            double* rvec, double* tvec, double* euler, double* reproject);
+
 /* ---- FaceAna.run for many concurrent video streams (csrc/mpipe.cu) ---------------------------------
  * What one FaceAna instance per stream does on the host in the reference (facer.py:52-85 with GroupTrack / OneEuroFilter /
  * EmaFilter of Skps/core/smoother/lk.py:6-162) happens here for up to n_streams streams per call with all per-stream state

@@ -15,6 +15,7 @@ SOURCES = {
     "engine.cu": [],
     "pipeline.cu": [],
     "mpipe.cu": [],
+    "headpose.cu": [],
     "temporal.cu": ["-fmad=false"],  # float64 arithmetic must round like numpy's (no contraction)
     "conv_simt.cu": [],
     "conv_tc.cu": [],

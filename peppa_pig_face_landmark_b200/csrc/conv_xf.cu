@@ -98,7 +98,7 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < XF_RING; ++s) {
             mbar_init(smem_u32(&raw_full[s]), 1);
-            mbar_init(smem_u32(&raw_empty[s]), 4);           // one arrival per warp of the half that consumes the slot
+            mbar_init(smem_u32(&raw_empty[s]), p.halves ? 4 : 8);   // one arrival per warp that consumes the slot
             mbar_init(smem_u32(&a_raw[s]), 1);
             mbar_init(smem_u32(&a_full[s]), 8);
             mbar_init(smem_u32(&a_empty[s]), 1);
@@ -275,6 +275,78 @@ conv_xf_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
                         }
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad + (uint32_t)XF_A_PLANE), "r"(lv[0]), "r"(lv[1]), "r"(lv[2]), "r"(lv[3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&a_full[ast]));
+                    if (++ast == p.as) { ast = 0; aph ^= 1u; }
+                }
+            }
+        } else if (!p.halves) {
+            // layers without up-sampled channels: all 256 threads work on one 32-channel sub-chunk at a time,
+            // thread = 4 consecutive output pixels of one tile row x 4 channels
+            const int cl = tt & 7, pg = tt >> 3, prow = pg >> 2, xs = (pg & 3) * 4;
+            const float* dws = reinterpret_cast<const float*>(smem_raw + (w_off - smem_u32(smem_raw)));
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int t = tile % p.tiles_per_img;
+                const int oy0 = (t / p.tiles_x) * XF_TH, ox0 = (t % p.tiles_x) * XF_TW;
+                const int oy = oy0 + prow, ox = ox0 + xs;
+                for (int kc = 0; kc < p.cchunks; ++kc) {
+                    mbar_wait_g(smem_u32(&a_empty[ast]), aph ^ 1u);
+                    const uint32_t sa = a_off + (uint32_t)ast * XF_A_BYTES;
+                    const int subs = p.chunk_subs[kc];
+                    for (int h = 0; h < subs; ++h) {
+                        const int sm = p.sub_mode[kc * 2 + h];
+                        const int cw = kc * 64 + h * 32 + cl * 4;
+                        const float4 bias4 = *reinterpret_cast<const float4*>(dws + 9 * Kpad + cw);
+                        float4 acc[4] = {bias4, bias4, bias4, bias4};
+                        mbar_wait_g(smem_u32(&raw_full[rst]), rph);
+                        const uint8_t* raw = smem_raw + (r_off + (uint32_t)rst * XF_RAW_BYTES - smem_u32(smem_raw));
+                        {
+#pragma unroll
+                            for (int ky = 0; ky < 3; ++ky) {
+                                float4 in[6];
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) {
+                                    const int px = (prow + ky) * XF_IW + xs + i;
+                                    if (sm == XS_DW_F32) {
+                                        in[i] = *reinterpret_cast<const float4*>(raw + (px * 32 + cl * 4) * 4);
+                                    } else {
+                                        const uint2 a = *reinterpret_cast<const uint2*>(raw + (px * 32 + cl * 4) * 2);
+                                        const uint2 b = *reinterpret_cast<const uint2*>(raw + XF_RAW_BYTES / 2 + (px * 32 + cl * 4) * 2);
+                                        const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+                                        const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+                                        const float2 b01 = __half22float2(*reinterpret_cast<const __half2*>(&b.x));
+                                        const float2 b23 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+                                        in[i] = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+                                    }
+                                }
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const float4 w = *reinterpret_cast<const float4*>(dws + (ky * 3 + kx) * Kpad + cw);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) acc[q] = f4_fma(in[q + kx], w, acc[q]);
+                                }
+                            }
+                        }
+                        // the raw tile has been consumed into registers: hand the slot back to the TMA producer
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&raw_empty[rst]));
+                        if (++rst == p.rs) { rst = 0; rph ^= 1u; }
+                        // activation, fp16 hi/lo split, store into the swizzled K-major A tile
+                        const int jc = h * 4 + (cl >> 1);                    // logical 16-byte chunk of the 128-byte row
+                        switch (p.dw_act) {               // one branch per sub-chunk, not one per element
+                            case ACT_RELU: act16<ACT_RELU>(acc); break;
+                            case ACT_HSWISH: act16<ACT_HSWISH>(acc); break;
+                            case ACT_SILU: act16<ACT_SILU>(acc); break;
+                            default: break;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 v = acc[q];
+                            const int r = prow * XF_TW + xs + q;
+                            split_store4(sa + (uint32_t)r * 128u + (uint32_t)((jc ^ (r & 7)) << 4) + (uint32_t)(cl & 1) * 8u, v);
+                        }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -635,6 +707,7 @@ int xf_prepare(XfLayer& L, const XfSetup& s) {
     if (k.nsplit == 2 && (s.n_tile % 32)) k.nsplit = 1;          // halves must stay multiples of 16
     k.n_sub = s.n_tile / k.nsplit;
     k.dw_act = s.dw_act;
+    k.halves = s.low.base ? 1 : 0;
     k.Hl = s.low.base ? s.low.H : 0; k.Wl = s.low.base ? s.low.W : 0;
     for (int kc = 0; kc < k.cchunks; ++kc) {
         const int valid = k.Cin - kc * 64 < 64 ? k.Cin - kc * 64 : 64;

@@ -21,6 +21,7 @@ struct XfK {
     int rs, as, bs, out_bufs;                       // ring depths: raw tiles, A tiles, B tiles, epilogue staging buffers
     int dw_act;                                     // activation between the depthwise stage and the pointwise conv
     int Hl, Wl;                                     // low-res map of the up-sampled channels (XS_UP_F32)
+    int halves;                                     // transform mapping: 1 = two halves x 2-row patches (layers with up-sampled channels)
     int wcx;                                        // column classes per staged weight block: 3, or 4 when the map is one tile wide
     uint8_t sub_mode[2 * XF_MAX_CHUNKS];            // per 32-channel sub-chunk
     int16_t sub_c[2 * XF_MAX_CHUNKS];               // channel coordinate of the sub-chunk in its source tensor

@@ -136,6 +136,52 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------
+// Rectangular crop + resize of one image (WFLW evaluation, TRAIN/face_landmark/tools/eval_WFLW.py:38-80,113-124:
+// copyMakeBorder(zero) -> img[min_y:max_y, min_x:max_x] -> cv2.resize((S, S))).  rect = [x0, y0, w, h] in frame
+// coordinates; pixels outside the frame are the zero border.  Same fixed-point bilinear as above, bit-exact with OpenCV.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rect_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, int pitch,
+                                                          int rx, int ry, int rw, int rh, uint8_t* __restrict__ out, int S) {
+    const int y = blockIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= S) return;
+    uint8_t* o = out + ((long long)y * S + x) * 3;
+    Tap tx = linear_tap(x, S, rw, true);
+    Tap ty = linear_tap(y, S, rh, false);
+    int fx0 = rx + tx.i0, fx1 = rx + tx.i1, fy0 = ry + ty.i0, fy1 = ry + ty.i1;
+    bool vx0 = fx0 >= 0 && fx0 < W, vx1 = fx1 >= 0 && fx1 < W;
+    bool vy0 = fy0 >= 0 && fy0 < H, vy1 = fy1 >= 0 && fy1 < H;
+    const uint8_t* r0 = frame + (long long)(vy0 ? fy0 : 0) * pitch;
+    const uint8_t* r1 = frame + (long long)(vy1 ? fy1 : 0) * pitch;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int p00 = (vy0 && vx0) ? r0[fx0 * 3 + c] : 0, p01 = (vy0 && vx1) ? r0[fx1 * 3 + c] : 0;
+        int p10 = (vy1 && vx0) ? r1[fx0 * 3 + c] : 0, p11 = (vy1 && vx1) ? r1[fx1 * 3 + c] : 0;
+        o[c] = (uint8_t)vblend(p00 * tx.w0 + p01 * tx.w1, p10 * tx.w0 + p11 * tx.w1, ty.w0, ty.w1);
+    }
+}
+
+// Normalised mean error per face (eval_WFLW.py:84-95): mean_p |pred_p - gt_p| / |gt_60 - gt_72| (inter-ocular), float32
+// like numpy's; one warp per face.
+__global__ void nme_kernel(const float* __restrict__ target, const float* __restrict__ preds, int n, int P, int ia, int ib,
+                           float* __restrict__ out) {
+    const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (f >= n) return;
+    const float* t = target + (long long)f * P * 2;
+    const float* q = preds + (long long)f * P * 2;
+    float s = 0.f;
+    for (int p = lane; p < P; p += 32) {
+        const float dx = q[2 * p] - t[2 * p], dy = q[2 * p + 1] - t[2 * p + 1];
+        s += sqrtf(dx * dx + dy * dy);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        const float nx = t[2 * ia] - t[2 * ib], ny = t[2 * ia + 1] - t[2 * ib + 1];
+        out[f] = (s / (float)P) / sqrtf(nx * nx + ny * ny);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Detector post-processing (face_detector.py:31-37, 73-136).  One block.
 //   1. rows with obj > score_thres -> xyxy candidates (more than MAXC: count = -candidates, nothing else written)
 //   2. order = (score desc, row index desc)  [np.argsort(score)[::-1]; ties measure-zero]
@@ -431,6 +477,24 @@ extern "C" SKPS_API int skps_crop_resize(const uint8_t* frame, int H, int W, int
     dim3 grid((out_hw + 255) / 256, out_hw, max_faces);
     crop_resize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frame, H, W, pitch, boxes4, count, face_scale,
                                                                min_face, crops, out_hw, detail);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" SKPS_API int skps_crop_rect(const uint8_t* frame, int H, int W, int pitch, int rx, int ry, int rw, int rh,
+                                       uint8_t* out, int out_hw, void* stream) {
+    SKPS_CHECK(frame && out && H > 0 && W > 0 && rw > 0 && rh > 0 && out_hw > 0, "crop_rect: bad arguments");
+    dim3 grid((out_hw + 255) / 256, out_hw);
+    rect_resize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(frame, H, W, pitch, rx, ry, rw, rh, out, out_hw);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" SKPS_API int skps_nme(const float* target, const float* preds, int n, int n_points, int norm_a, int norm_b,
+                                 float* out, void* stream) {
+    SKPS_CHECK(target && preds && out && n > 0 && n_points > 0 && norm_a >= 0 && norm_b >= 0 && norm_a < n_points &&
+               norm_b < n_points, "nme: bad arguments");
+    nme_kernel<<<(n + 3) / 4, 128, 0, (cudaStream_t)stream>>>(target, preds, n, n_points, norm_a, norm_b, out);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

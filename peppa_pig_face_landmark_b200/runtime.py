@@ -74,6 +74,9 @@ SIGNATURES = {
     "skps_pipeline_run": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_float, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                     c_vp]),
+    "skps_crop_rect": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp]),
+    "skps_nme": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
+    "skps_head_pose": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "skps_mpipe_create": (C.c_int, [c_vp, c_vp, C.POINTER(PipelineCfg), C.c_int, C.POINTER(c_vp)]),
     "skps_mpipe_destroy": (None, [c_vp]),
     "skps_mpipe_reset": (C.c_int, [c_vp, C.c_int]),
