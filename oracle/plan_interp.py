@@ -52,7 +52,10 @@ class PlanInterp:
         def wr(v, val):
             bufs[v.buf.idx][..., v.c_off: v.c_off + v.C * v.c_stride: v.c_stride] = val
 
-        for op in pl.ops:
+        ops = []
+        for op in pl.ops:                       # a fused stem block is executed as the layers it replaces
+            ops += op.sub_ops if op.type == P.OP_STEM_BLOCK else [op]
+        for op in ops:
             t = op.type
             if t == P.OP_CONV:
                 x = rd(op.ins[0])

@@ -11,7 +11,7 @@ namespace skps {
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
-    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14, OP_SE_FC = 15, OP_DWPW = 16
+    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14, OP_SE_FC = 15, OP_DWPW = 16, OP_STEM_BLOCK = 17
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo

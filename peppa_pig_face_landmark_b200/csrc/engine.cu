@@ -16,6 +16,7 @@
 #include "conv_tc.h"
 #include "conv_xf.h"
 #include "dw_tma.h"
+#include "stem_block.h"
 
 namespace skps {
 
@@ -142,6 +143,24 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 break;
             }
             case OP_DWPW: rc = xf_launch(e->xf[i], batch, b0, e->num_sms, s); break;
+            case OP_STEM_BLOCK: {
+                // w = StemBlockW as packed by lowering (dense weights -> kernel-parameter bank); i[0] -> [9][E]+[E] depthwise table
+                StemBlockW W;
+                memcpy(&W, e->h_weights.data() + op.w_off, sizeof(W));
+                StemBlockK k;
+                k.in = (const uint8_t*)in0.base;
+                k.H = in0.H; k.W = in0.W; k.Hq = out0.H; k.Wq = out0.W;
+                k.img0 = 0; k.n_tiles = batch * (out0.H / 8) * (out0.W / 16);
+                k.dw1 = e->d_weights + op.i[0];
+                k.out = out0.base; k.out_fmt = out0.fmt; k.out_plane = out0.plane; k.out_ld = out0.ld; k.out_coff = out0.c_off;
+                if (e->f32_mode || in0.fmt != DT_U8 || !stem_block_supported(in0.H, in0.W, out0.C, out0)) {
+                    set_error("stem block: needs the uint8 input path and a supported shape");
+                    rc = 1;
+                    break;
+                }
+                rc = stem_block_launch(k, W, e->num_sms, s);
+                break;
+            }
             case OP_MAXPOOL2: rc = launch_maxpool2(in0, out0, batch, s); break;
             case OP_RESIZE_NEAREST: rc = launch_resize_nearest(in0, out0, batch, s); break;
             case OP_UPSAMPLE_BILINEAR2X: rc = launch_bilinear2x(in0, out0, batch, s); break;

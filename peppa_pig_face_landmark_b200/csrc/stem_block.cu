@@ -1,0 +1,259 @@
+// The full-resolution head of the landmark encoder as ONE kernel (sm_100a, CUDA cores, float32):
+//
+//   uint8 crop (H x W x 3)  -> conv_stem 3x3 s2 (+/255, h-swish)                        16 ch @ H/2      [kps_student.onnx
+//                           -> blocks.0.0: depthwise 3x3 + ReLU -> 1x1 16->16 + shortcut 16 ch @ H/2       /student/encoder/
+//                           -> blocks.1.0: 1x1 16->E + ReLU -> depthwise 3x3 s2 + ReLU   E ch @ H/4        conv_stem .. blocks.1.0/conv_dw]
+//
+// (timm mobilenetv3 stem + DepthwiseSeparable block + the expand/depthwise half of the first InvertedResidual;
+// TRAIN/face_landmark/lib/core/base_trainer/model.py:247-262.)  Run as separate launches these four layers move 3.5 GB
+// of 16- and 64-channel full-resolution tensors through HBM per 256-face batch (1.17 ms of a 7 ms step, r2 launch list);
+// fused, a CTA reads a 39 x 71 pixel window of the crop and writes an 8 x 16 tile of the E-channel quarter-resolution
+// tensor, everything in between lives in shared memory.  The work is ~1.2 M FMAs per tile on tensors with 3 / 16 input
+// channels - too thin for 128 x N x 16 tensor-core tiles - so it runs on the FP32 pipes with every dense weight taken from
+// the kernel-parameter (constant) bank: the unrolled inner loops issue FFMA with a constant operand and read each
+// activation from shared memory once per 16 outputs.
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include "common.h"
+#include "stem_block.h"
+
+namespace skps {
+
+constexpr int SB_THREADS = 576;
+constexpr int SB_TH = 8, SB_TW = 16;                       // output tile (quarter resolution)
+constexpr int SB_EH = 2 * SB_TH + 1, SB_EW = 2 * SB_TW + 1;   // 17 x 33: half-resolution window the stride-2 depthwise reads
+constexpr int SB_SH = SB_EH + 2, SB_SW = SB_EW + 2;        // 19 x 35: stem outputs the 3x3 depthwise of block 0 reads
+constexpr int SB_IH = 2 * SB_SH + 1, SB_IW = 2 * SB_SW + 1;   // 39 x 71: input pixels the stem reads
+constexpr int SB_PS = 20;                                  // floats per pixel in shared memory (16 + pad: conflict-free float4 rows)
+constexpr int SB_NE = SB_EH * SB_EW, SB_NS = SB_SH * SB_SW, SB_NI = SB_IH * SB_IW;
+constexpr int SB_A_FLOATS = (SB_NI * 4 > SB_NE * SB_PS) ? SB_NI * 4 : SB_NE * SB_PS;    // input window, later block-0 depthwise output
+constexpr int SB_B_FLOATS = SB_NS * SB_PS;                 // stem output, later one 16-channel chunk of the expanded tensor
+constexpr int SB_C_FLOATS = SB_NE * SB_PS;                 // block-0 output
+constexpr int SB_SMEM = (SB_A_FLOATS + SB_B_FLOATS + SB_C_FLOATS + 10 * SB_MAX_E + 256) * 4;
+
+__device__ __forceinline__ float hswish_f(float v) { return v * hsigmoid_f(v); }
+
+// block-0 depthwise: 4 consecutive pixels of one window row x channel group G (weights as constant operands)
+template <int G>
+__device__ __forceinline__ void dw16_strip(const float* __restrict__ s1, float* __restrict__ s2, int row, int x0, const StemBlockW& Wt) {
+    float4 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(Wt.dw0_b[4 * G], Wt.dw0_b[4 * G + 1], Wt.dw0_b[4 * G + 2], Wt.dw0_b[4 * G + 3]);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        float4 in[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int xx = min(x0 + i, SB_SW - 1);          // the last strip of a row hangs over by up to 3 columns
+            in[i] = *reinterpret_cast<const float4*>(s1 + ((row + ky) * SB_SW + xx) * SB_PS + 4 * G);
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int t = ky * 3 + kx;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q].x = fmaf(in[q + kx].x, Wt.dw0_w[t * 16 + 4 * G], acc[q].x);
+                acc[q].y = fmaf(in[q + kx].y, Wt.dw0_w[t * 16 + 4 * G + 1], acc[q].y);
+                acc[q].z = fmaf(in[q + kx].z, Wt.dw0_w[t * 16 + 4 * G + 2], acc[q].z);
+                acc[q].w = fmaf(in[q + kx].w, Wt.dw0_w[t * 16 + 4 * G + 3], acc[q].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (x0 + q >= SB_EW) break;
+        float4 v = acc[q];
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        *reinterpret_cast<float4*>(s2 + (row * SB_EW + x0 + q) * SB_PS + 4 * G) = v;
+    }
+}
+
+// one 16-output slice of a 1x1 conv on a 16-channel pixel: acc[j] = b[j] + sum_ci x[ci] * w[ci][j] (constant operands)
+template <int CO, int OFF>
+__device__ __forceinline__ void pw16in(const float* __restrict__ x, const float* w, const float* b, float* acc) {
+    float in[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(x + 4 * g);
+        in[4 * g] = v.x; in[4 * g + 1] = v.y; in[4 * g + 2] = v.z; in[4 * g + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = b[OFF + j];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[ci], w[ci * CO + OFF + j], acc[j]);
+}
+
+template <int E>
+__global__ void __launch_bounds__(SB_THREADS, 1)
+stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
+    extern __shared__ __align__(16) float sm[];
+    float* sA = sm;                                    // input window (float4 per pixel: b, g, r, 0), later s2
+    float* sB = sA + SB_A_FLOATS;                      // stem output s1, later the expanded chunk
+    float* sC = sB + SB_B_FLOATS;                      // block-0 output s3
+    float* sW = sC + SB_C_FLOATS;                      // stride-2 depthwise weights [9][E] + bias [E]
+    float* lut = sW + 10 * SB_MAX_E;                   // i / 255
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += SB_THREADS) lut[i] = __fdiv_rn((float)i, 255.f);
+    for (int i = tid; i < 10 * E; i += SB_THREADS) sW[i] = p.dw1[i];
+    const int tiles_x = p.Wq / SB_TW, tiles_per_img = tiles_x * (p.Hq / SB_TH);
+    const int Hh = p.H / 2, Wh = p.W / 2;              // half-resolution map
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int img_l = tile / tiles_per_img, t = tile - img_l * tiles_per_img, img = img_l + p.img0;
+        const int oy0 = (t / tiles_x) * SB_TH, ox0 = (t % tiles_x) * SB_TW;     // quarter-res origin of the tile
+        const int ey0 = 2 * oy0 - 1, ex0 = 2 * ox0 - 1;       // half-res origin of the 17 x 33 window
+        const int sy0 = ey0 - 1, sx0 = ex0 - 1;               // half-res origin of the 19 x 35 stem window
+        const int iy0 = 2 * sy0 - 1, ix0 = 2 * sx0 - 1;       // input origin of the 39 x 71 window
+        // ---- S0: input window, /255 (true division, as numpy does), zero outside the crop (the stem's padding)
+        const uint8_t* src = p.in + (long long)img * p.H * p.W * 3;
+        for (int i = tid; i < SB_NI; i += SB_THREADS) {
+            const int r = i / SB_IW, c = i - r * SB_IW, y = iy0 + r, x = ix0 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                const uint8_t* px = src + ((long long)y * p.W + x) * 3;
+                v.x = lut[px[0]]; v.y = lut[px[1]]; v.z = lut[px[2]];
+            }
+            *reinterpret_cast<float4*>(sA + 4 * i) = v;
+        }
+        __syncthreads();
+        // ---- S1: stem 3x3 stride 2 + h-swish over the 19 x 35 window; item = (pixel, 8 output channels)
+        for (int it = tid; it < 2 * ((SB_NS + 31) / 32) * 32; it += SB_THREADS) {
+            const int hf = (it >> 5) & 1, px = ((it >> 6) << 5) | (it & 31);       // the channel half is warp-uniform
+            if (px >= SB_NS) continue;
+            const int r = px / SB_SW, c = px - r * SB_SW;
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            const int y = sy0 + r, x = sx0 + c;
+            const bool inside = y >= 0 && y < Hh && x >= 0 && x < Wh;
+            if (inside) {
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 v = *reinterpret_cast<const float4*>(sA + 4 * ((2 * r + ky) * SB_IW + 2 * c + kx));
+                        const int tp = (ky * 3 + kx) * 3;
+                        if (hf == 0) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                acc[j] = fmaf(v.x, Wt.stem_w[(tp + 0) * 16 + j], acc[j]);
+                                acc[j] = fmaf(v.y, Wt.stem_w[(tp + 1) * 16 + j], acc[j]);
+                                acc[j] = fmaf(v.z, Wt.stem_w[(tp + 2) * 16 + j], acc[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                acc[j] = fmaf(v.x, Wt.stem_w[(tp + 0) * 16 + 8 + j], acc[j]);
+                                acc[j] = fmaf(v.y, Wt.stem_w[(tp + 1) * 16 + 8 + j], acc[j]);
+                                acc[j] = fmaf(v.z, Wt.stem_w[(tp + 2) * 16 + 8 + j], acc[j]);
+                            }
+                        }
+                    }
+                if (hf == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = hswish_f(acc[j] + Wt.stem_b[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = hswish_f(acc[j] + Wt.stem_b[8 + j]);
+                }
+            }
+            // outside the half-resolution map the tensor is the NEXT conv's zero padding, not stem(padding)
+            float* o = sB + px * SB_PS + 8 * hf;
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        __syncthreads();
+        // ---- S2: blocks.0.0 depthwise 3x3 + ReLU over the 17 x 33 window; item = (4-pixel strip, 4-channel group)
+        {
+            constexpr int STRIPS = (SB_EW + 3) / 4;            // 9 strips per row, the last one 1 pixel wide
+            for (int it = tid; it < SB_EH * STRIPS * 4; it += SB_THREADS) {
+                const int g = it & 3, sidx = it >> 2, row = sidx / STRIPS, x0 = (sidx - row * STRIPS) * 4;
+                switch (g) {
+                    case 0: dw16_strip<0>(sB, sA, row, x0, Wt); break;
+                    case 1: dw16_strip<1>(sB, sA, row, x0, Wt); break;
+                    case 2: dw16_strip<2>(sB, sA, row, x0, Wt); break;
+                    default: dw16_strip<3>(sB, sA, row, x0, Wt); break;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- S3: blocks.0.0 pointwise 16->16 (linear) + shortcut (the stem output at the same pixel) -> s3
+        for (int px = tid; px < SB_NE; px += SB_THREADS) {
+            const int r = px / SB_EW, c = px - r * SB_EW;
+            float acc[16];
+            pw16in<16, 0>(sA + px * SB_PS, Wt.pw0_w, Wt.pw0_b, acc);
+            const float* res = sB + ((r + 1) * SB_SW + c + 1) * SB_PS;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const float4 rv = *reinterpret_cast<const float4*>(res + 4 * g);
+                *reinterpret_cast<float4*>(sC + px * SB_PS + 4 * g) =
+                    make_float4(acc[4 * g] + rv.x, acc[4 * g + 1] + rv.y, acc[4 * g + 2] + rv.z, acc[4 * g + 3] + rv.w);
+            }
+        }
+        __syncthreads();
+        // ---- S4/S5 per 16-channel chunk of the expanded tensor: 1x1 16->E + ReLU into sB, then depthwise 3x3 s2 + ReLU
+        const int y_ok0 = max(0, -ey0), y_ok1 = min(SB_EH, Hh - ey0), x_ok0 = max(0, -ex0), x_ok1 = min(SB_EW, Wh - ex0);
+#pragma unroll
+        for (int ch = 0; ch < E / 16; ++ch) {
+            for (int px = tid; px < SB_NE; px += SB_THREADS) {
+                const int r = px / SB_EW, c = px - r * SB_EW;
+                float acc[16];
+                if (ch == 0) pw16in<E, 0>(sC + px * SB_PS, Wt.pw1_w, Wt.pw1_b, acc);
+                else if (ch == 1) pw16in<E, 16>(sC + px * SB_PS, Wt.pw1_w, Wt.pw1_b, acc);
+                else if (ch == 2) pw16in<E, 32>(sC + px * SB_PS, Wt.pw1_w, Wt.pw1_b, acc);
+                else pw16in<E, 48>(sC + px * SB_PS, Wt.pw1_w, Wt.pw1_b, acc);
+                // zero outside the half-resolution map: the stride-2 depthwise's padding
+                const bool inside = r >= y_ok0 && r < y_ok1 && c >= x_ok0 && c < x_ok1;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<float4*>(sB + px * SB_PS + 4 * g) = inside
+                        ? make_float4(fmaxf(acc[4 * g], 0.f), fmaxf(acc[4 * g + 1], 0.f), fmaxf(acc[4 * g + 2], 0.f), fmaxf(acc[4 * g + 3], 0.f))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
+            // depthwise 3x3 stride 2: item = (output pixel, 4-channel group) = 128 x 4 = 512 items
+            if (tid < SB_TH * SB_TW * 4) {
+                const int g = tid & 3, opx = tid >> 2, orow = opx / SB_TW, ocol = opx - orow * SB_TW;
+                const int c0 = ch * 16 + 4 * g;
+                float4 acc = *reinterpret_cast<const float4*>(sW + 9 * E + c0);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float4 v = *reinterpret_cast<const float4*>(sB + ((2 * orow + ky) * SB_EW + 2 * ocol + kx) * SB_PS + 4 * g);
+                        const float4 w = *reinterpret_cast<const float4*>(sW + (ky * 3 + kx) * E + c0);
+                        acc.x = fmaf(v.x, w.x, acc.x); acc.y = fmaf(v.y, w.y, acc.y);
+                        acc.z = fmaf(v.z, w.z, acc.z); acc.w = fmaf(v.w, w.w, acc.w);
+                    }
+                acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                const long long o = (((long long)img * p.Hq + oy0 + orow) * p.Wq + ox0 + ocol) * p.out_ld + p.out_coff + c0;
+                st4(p.out, p.out_fmt, p.out_plane, o, acc);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+bool stem_block_supported(int H, int W, int E, const TView& out) {
+    if (H % 32 || W % 64 || (E != 64)) return false;          // whole 8 x 16 quarter-resolution tiles; E fixed by the template
+    return out.base && out.c_stride == 1 && out.C == E && out.H == H / 4 && out.W == W / 4 && !((out.ld | out.c_off) & 3) &&
+           (out.fmt == DT_F32 || out.fmt == DT_SPLIT16);
+}
+
+int stem_block_launch(const StemBlockK& k, const StemBlockW& w, int num_sms, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SKPS_CUDA(cudaFuncSetAttribute(stem_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+        attr_set = true;
+    }
+    const int grid = k.n_tiles < num_sms ? k.n_tiles : num_sms;
+    stem_block_kernel<64><<<grid, SB_THREADS, SB_SMEM, s>>>(k, w);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace skps

@@ -973,6 +973,56 @@ def _fuse_dw_pw(pl):
         pl.ops.remove(d)
 
 
+def _fuse_stem_block(pl):
+    """uint8 input -> conv_stem 3x3 s2 (h-swish) -> [depthwise 3x3 + ReLU -> 1x1 16->16 + shortcut] -> 1x1 16->64 + ReLU ->
+    depthwise 3x3 s2 + ReLU: the whole full-resolution head of the mobilenetv3 encoder (kps_student.onnx conv_stem,
+    blocks.0.0, blocks.1.0/conv_pw + conv_dw) becomes ONE CUDA-core kernel (csrc/stem_block.cu); the 16- and 64-channel
+    full-resolution tensors never reach HBM."""
+    if os.environ.get("SKPS_STEM_BLOCK", "1") == "0" or len(pl.ops) < 4:
+        return
+    c0, b0, c1, d1 = pl.ops[0], pl.ops[1], pl.ops[2], pl.ops[3]
+
+    def same(a, b):
+        return a is not None and b is not None and a.buf is b.buf and (a.c_off, a.c_stride, a.C) == (b.c_off, b.c_stride, b.C)
+
+    def whole(v):
+        return v.c_off == 0 and v.c_stride == 1 and v.C == v.buf.C
+
+    def single_use(v, users):
+        return all(not any(i is not None and i.buf is v.buf for i in o.ins) for o in pl.ops if o not in users) \
+            and v.buf not in [o.buf for o in pl.outputs]
+
+    H, W = pl.input.buf.H, pl.input.buf.W
+    ok = (c0.type == P.OP_CONV and (c0.flags & P.FLAG_IN_U8) and list(c0.k) == [3, 3] and list(c0.s) == [2, 2]
+          and list(c0.p) == [1, 1] and c0.act == P.ACT_HSWISH and c0.outs[0].C == 16 and whole(c0.outs[0])
+          and c0.ins[1] is None and c0.b is not None
+          and b0.type == P.OP_DWPW and b0.ins[2] is None and same(b0.ins[0], c0.outs[0]) and same(b0.ins[1], c0.outs[0])
+          and int(b0.dw_act) == P.ACT_RELU and b0.act == P.ACT_NONE and b0.outs[0].C == 16 and whole(b0.outs[0])
+          and not (b0.flags & P.FLAG_RES_FIRST)
+          and c1.type == P.OP_CONV and list(c1.k) == [1, 1] and list(c1.s) == [1, 1] and same(c1.ins[0], b0.outs[0])
+          and c1.ins[1] is None and c1.ins[2] is None and c1.act == P.ACT_RELU and c1.outs[0].C == 64 and whole(c1.outs[0])
+          and d1.type == P.OP_DWCONV and list(d1.k) == [3, 3] and list(d1.s) == [2, 2] and list(d1.p) == [1, 1]
+          and list(d1.d) == [1, 1] and d1.act == P.ACT_RELU and same(d1.ins[0], c1.outs[0]) and len(d1.outs) == 1
+          and d1.outs[0].c_stride == 1 and not ((d1.outs[0].buf.C | d1.outs[0].c_off) & 3)
+          and H % 32 == 0 and W % 64 == 0
+          and single_use(c0.outs[0], [b0]) and single_use(b0.outs[0], [c1]) and single_use(c1.outs[0], [d1]))
+    if not ok:
+        return
+    E = 64
+    sw = np.ascontiguousarray(c0.w_ref.transpose(1, 2, 3, 0).reshape(27, 16), np.float32)         # [(ky*3+kx)*3+ci][co]
+    pw0 = np.ascontiguousarray(b0.w_ref.reshape(16, 16).T, np.float32)                              # [ci][co]
+    pw1 = np.ascontiguousarray(c1.w_ref.reshape(E, 16).T, np.float32)                               # [ci][co]
+    zeros = lambda n: np.zeros(n, np.float32)
+    packed = np.concatenate([sw.reshape(-1), c0.b, b0.dw_w.reshape(-1), b0.dw_b, pw0.reshape(-1),
+                             b0.b if b0.b is not None else zeros(16), pw1.reshape(-1),
+                             c1.b if c1.b is not None else zeros(E)]).astype(np.float32)
+    assert packed.size == 27 * 16 + 16 + 144 + 16 + 256 + 16 + 16 * E + E
+    o = P.Op(P.OP_STEM_BLOCK, [pl.input], [d1.outs[0]], P.ACT_RELU, w=packed, name="stem_block:" + d1.name)
+    o.extra = np.concatenate([d1.w.reshape(9, E), d1.b.reshape(1, E)]).astype(np.float32)           # [9][E] + [E]
+    o.sub_ops = [c0, b0, c1, d1]                  # the layers it replaces (oracle/plan_interp.py executes these)
+    pl.ops[0:4] = [o]
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -985,6 +1035,8 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
         _fuse_se_chain(lw.plan)
     if use_tc:
         _fuse_dw_pw(lw.plan)
+        if input_u8:
+            _fuse_stem_block(lw.plan)
     chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
     if chunk_env not in ("0", ""):
         lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)

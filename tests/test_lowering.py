@@ -123,7 +123,12 @@ def test_student_plan_fusions():
     assert kinds.count(P.OP_SE_FC) == 8 and kinds.count(P.OP_GAP) == 2
     assert kinds.count(P.OP_UPCAT_DW) == 0 and kinds.count(P.OP_SCALE_CH) == 0
     fused = [o for o in plan.ops if o.type == P.OP_DWPW]
-    assert len(fused) == 7 and sum(1 for o in fused if o.ins[2] is not None) == 2          # 5 encoder pairs + 2 decoder heads
+    assert len(fused) == 6 and sum(1 for o in fused if o.ins[2] is not None) == 2          # 4 encoder pairs + 2 decoder heads
+    # the full-resolution head (stem, blocks.0.0, blocks.1.0 expand + stride-2 depthwise) is one op on the uint8 input
+    sb = plan.ops[0]
+    assert sb.type == P.OP_STEM_BLOCK and sb.ins[0].buf is plan.input.buf and sb.outs[0].C == 64 and sb.outs[0].H == 64
+    assert sb.w.size == 27 * 16 + 16 + 144 + 16 + 256 + 16 + 1024 + 64 and sb.extra.shape == (10, 64) and len(sb.sub_ops) == 4
+    assert sum(1 for o in plan.ops if o.type == P.OP_STEM_BLOCK) == 1
     for o in fused:
         K = o.ins[0].C + (o.ins[2].C if o.ins[2] is not None else 0)
         assert o.extra.shape == (10, -(-K // 64) * 64) and o.extra_slot == 3 and o.w.shape[1] == o.extra.shape[1]
