@@ -15,7 +15,7 @@ enum OpType {
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
-enum { FLAG_IN_U8 = 1, FLAG_TC = 2, FLAG_RES_FIRST = 4, FLAG_GAP_PARTIAL = 8, FLAG_MMA = 16, FLAG_XF = 32 };
+enum { FLAG_IN_U8 = 1, FLAG_TC = 2, FLAG_RES_FIRST = 4, FLAG_GAP_PARTIAL = 8, FLAG_MMA = 16, FLAG_XF = 32, FLAG_HM_PART = 64 };
 enum { OP_WORDS = 64, PLAN_MAGIC = 0x534B5053 };
 
 struct View {            // 6 words
@@ -227,7 +227,8 @@ int launch_addn(const TView* ins, int n_in, const TView& out, int act, int batch
 int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const float* b1, const float* w2t, const float* b2,
                  int Cr, int act1, int act2, int hw, int batch, cudaStream_t s);
 // feat.base != null: hm holds the score maps only and the x/y offsets are w_off/b_off ([2P][K], [2P]) applied to feat at the arg-max pixel
+// part != null: the head conv wrote per-tile (max, arg-max) rows instead of the map (FLAG_HM_PART); hm is then only its shape
 int launch_hm_decode(const TView& hm, const TView& feat, const float* w_off, const float* b_off, const TView& xy,
-                     const TView& score, int npts, int batch, cudaStream_t s);
+                     const TView& score, int npts, int batch, cudaStream_t s, const TView* part = nullptr);
 
 }  // namespace skps

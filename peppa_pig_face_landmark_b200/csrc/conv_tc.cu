@@ -34,6 +34,23 @@ constexpr int TC_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / sp
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 4;
 
+// One level of a warp reduce-scatter of per-column (max, first arg-max): 2N column candidates per lane in, N out; after the
+// levels 16, 8, 4, 2, 1 lane L holds column L reduced over the warp's 32 rows.  Ties keep the smaller pixel index.
+template <int N>
+__device__ __forceinline__ void argmax_scatter(float* v, int* id, int off, int lane) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const float keep = hi ? v[j + N] : v[j], snd = hi ? v[j] : v[j + N];
+        const int kid = hi ? id[j + N] : id[j], sid = hi ? id[j] : id[j + N];
+        const float r = __shfl_xor_sync(0xffffffffu, snd, off);
+        const int ri = __shfl_xor_sync(0xffffffffu, sid, off);
+        const bool take = r > keep || (r == keep && ri < kid);
+        v[j] = take ? r : keep;
+        id[j] = take ? ri : kid;
+    }
+}
+
 template <int ACT, bool OUT_SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -42,6 +59,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float hm_sv[8][32];                 // heat-map head: per-warp column maxima, combined across the 4 lane quarters
+    __shared__ int hm_si[8][32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -193,6 +212,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 const int co0 = co_tile + c0;
                 const int nvalid = min(min(32, p.n_tile - c0), p.Cout - co0);   // n_tile need not be a multiple of 32
+                if (p.hm_val) {
+                    // heat-map head (model.py:511-554 postp): only max and first arg-max of every score map are needed.
+                    // Scores = acc * scale + bias (no activation); reduce the tile's 128 pixels per channel here and write
+                    // (max, pixel index) per tile instead of the map (436 MB per 256-face batch that hm_decode re-read).
+                    int id[32];
+                    const int my = row_ok ? y * p.W + x : 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = (row_ok && j < nvalid) ? fmaf(v[j], p.out_scale, __ldg(p.bias + co0 + (j < nvalid ? j : 0))) : -INFINITY;
+                        id[j] = my;
+                    }
+                    argmax_scatter<16>(v, id, 16, lane); argmax_scatter<8>(v, id, 8, lane); argmax_scatter<4>(v, id, 4, lane);
+                    argmax_scatter<2>(v, id, 2, lane); argmax_scatter<1>(v, id, 1, lane);
+                    hm_sv[warp - 4][lane] = v[0];
+                    hm_si[warp - 4][lane] = id[0];
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
+                    if (q == 0) {
+                        float bv = hm_sv[half_id * 4][lane];
+                        int bi = hm_si[half_id * 4][lane];
+#pragma unroll
+                        for (int w2 = 1; w2 < 4; ++w2) {
+                            const float ov = hm_sv[half_id * 4 + w2][lane];
+                            const int oi = hm_si[half_id * 4 + w2][lane];
+                            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                        }
+                        if (lane < nvalid) {
+                            const long long o = ((long long)img * p.tiles_per_img + t) * p.hm_ld + co0 + lane;
+                            p.hm_val[o] = bv;
+                            p.hm_idx[o] = bi;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
+                    continue;
+                }
                 const long long o_el = pix * p.out_ld + p.out_coff + co0;
                 // vector path: whole groups of 8 channels (every Cout in the network but the 294-wide heat map and
                 // the 1-channel sSE map is a multiple of 8), unit channel stride, 16-byte aligned destination
@@ -481,6 +534,11 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     k.out_cstride = s.out_cstride;
     k.res = s.res; k.res_fmt = s.res_fmt; k.res_plane = s.res_plane; k.res_ld = s.res_ld; k.res_coff = s.res_coff;
     k.res_first = s.res ? s.res_first : 0;
+    k.hm_val = s.hm_val; k.hm_idx = s.hm_idx; k.hm_ld = s.hm_ld;
+    if (k.hm_val) {
+        SKPS_CHECK(k.ipt == 1 && s.act == ACT_NONE && !s.res && (Ho * Wo) % TC_BM == 0 && k.tiles_per_img * TC_BM == Ho * Wo,
+                   "conv_tc: heat-map partials need whole 128-pixel tiles, no activation, no residual");
+    }
     return 0;
 }
 

@@ -22,6 +22,8 @@ struct TcK {                     // kernel parameters
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
     const void* res; int res_fmt; long long res_plane; int res_ld, res_coff;
     int res_first;               // act(acc + bias + res) (ResNet/HRNet blocks) instead of act(acc + bias) + res
+    // heat-map head: instead of storing the map, the epilogue reduces every 128-pixel tile to per-channel (max, first arg-max)
+    float* hm_val; int* hm_idx; int hm_ld;      // [img][tile][hm_ld] each; null = store the map as usual
 };
 
 struct TcLayer {                 // prepared once per conv op at engine creation
@@ -43,6 +45,7 @@ struct TcSetup {
     void* out; int out_fmt; long long out_plane; int out_ld, out_coff, out_cstride;
     const void* res; int res_fmt; long long res_plane; int res_ld, res_coff;
     int res_first;
+    float* hm_val; int* hm_idx; int hm_ld;        // per-tile (max, arg-max) partials of the heat-map head, or null
 };
 
 bool tc_shape_ok(int Ho, int Wo, int Cin, int in_ld, int in_coff);

@@ -190,7 +190,11 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 rc = launch_det_decode(heads, e->h_weights.data() + op.w_off, out0, op.i[0], batch, s);
                 break;
             }
-            case OP_HM_DECODE: rc = launch_hm_decode(in0, in1, w, b, out0, out1, op.i[0], batch, s); break;
+            case OP_HM_DECODE: {
+                TView part = in2;                          // FLAG_HM_PART: per-tile (max, arg-max) rows from the head conv
+                rc = launch_hm_decode(in0, in1, w, b, out0, out1, op.i[0], batch, s, (op.flags & FLAG_HM_PART) ? &part : nullptr);
+                break;
+            }
             default: set_error("engine: unknown op type %d (op %zu)", op.type, i); return 1;
         }
         if (rc) {
@@ -305,6 +309,11 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         s.out_cstride = out0.c_stride;
         s.res = res.base; s.res_fmt = res.fmt; s.res_plane = res.plane; s.res_ld = res.ld; s.res_coff = res.c_off;
         s.res_first = (op.flags & FLAG_RES_FIRST) ? 1 : 0;
+        if (op.flags & FLAG_HM_PART) {
+            // out[1] = [tiles][2 * ld] per sample: ld maxima then ld arg-max indices; the map itself is not stored
+            TView part = resolve(e, op.out[1]);
+            s.hm_val = (float*)part.base; s.hm_idx = (int*)part.base + part.ld / 2; s.hm_ld = part.ld;
+        }
         if (op.dh != op.dw || op.ph != op.pw || tc_prepare(e->tc[i], s)) {
             char tmp[900];
             snprintf(tmp, sizeof(tmp), "%s", get_error());

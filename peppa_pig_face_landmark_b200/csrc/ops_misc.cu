@@ -1002,8 +1002,13 @@ struct HmOff {          // split head: offsets = rows P..3P of the 1x1 head conv
     const float* w; const float* b;                              // [2P][K], [2P]
 };
 
+struct HmPart {         // per-tile (max, first arg-max) written by the head conv's epilogue (conv_tc.cu): [n][tiles][ld]
+    const float* val; const int* idx; int tiles, ld;
+};
+
 __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld, int coff, int H, int W, int P,
-                                                         float* xy, int xy_ld, float* score, int sc_ld, const HmOff off) {
+                                                         float* xy, int xy_ld, float* score, int sc_ld, const HmOff off,
+                                                         const HmPart part) {
     __shared__ float sv[8][128];
     __shared__ int si[8][128];
     const int n = blockIdx.x;
@@ -1012,7 +1017,17 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
     const float* base = hm + (long long)n * HW * ld + coff;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    if (c < P) {
+    if (part.val) {
+        // tiles are in ascending pixel order and each holds its own first maximum: strict > keeps the first one overall
+        if (c < P) {
+            const int per = (part.tiles + 7) / 8, t0 = g * per, t1 = min(part.tiles, t0 + per);
+            for (int t = t0; t < t1; ++t) {
+                const long long o = ((long long)n * part.tiles + t) * part.ld + c;
+                const float v = part.val[o];
+                if (bi == 0x7fffffff || v > best) { best = v; bi = part.idx[o]; }
+            }
+        }
+    } else if (c < P) {
         int per = (HW + 7) / 8;
         int p0 = g * per, p1 = min(HW, p0 + per);
         for (int p = p0; p < p1; ++p) {
@@ -1073,9 +1088,17 @@ __global__ void __launch_bounds__(1024) hm_decode_kernel(const float* hm, int ld
 }
 
 int launch_hm_decode(const TView& hm, const TView& feat, const float* w_off, const float* b_off, const TView& xy,
-                     const TView& score, int npts, int batch, cudaStream_t s) {
+                     const TView& score, int npts, int batch, cudaStream_t s, const TView* part) {
     SKPS_CHECK((hm.C == 3 * npts || (hm.C == npts && feat.base)) && npts <= 128 && hm.c_stride == 1 && hm.H == hm.W &&
                hm.fmt == DT_F32, "hm_decode: shape/format");
+    HmPart hp = {};
+    if (part && part->base) {
+        // partial rows: [tiles][2 * ld] float32 per sample = ld maxima then ld arg-max indices (int32 bits)
+        SKPS_CHECK(feat.base && part->fmt == DT_F32 && part->c_stride == 1 && part->c_off == 0 && (part->ld & 1) == 0 &&
+                   part->ld / 2 >= npts, "hm_decode: partial-maximum view");
+        hp.val = (const float*)part->base; hp.idx = (const int*)part->base + part->ld / 2;
+        hp.tiles = part->H * part->W; hp.ld = part->ld;
+    }
     HmOff off = {};
     if (feat.base) {
         SKPS_CHECK(w_off && b_off && feat.c_stride == 1 && feat.H == hm.H && feat.W == hm.W &&
@@ -1085,7 +1108,7 @@ int launch_hm_decode(const TView& hm, const TView& feat, const float* w_off, con
     }
     dim3 block(128, 8);
     hm_decode_kernel<<<batch, block, 0, s>>>((const float*)hm.base, hm.ld, hm.c_off, hm.H, hm.W, npts,
-                                             (float*)xy.base, xy.ld, (float*)score.base, score.ld, off);
+                                             (float*)xy.base, xy.ld, (float*)score.base, score.ld, off, hp);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

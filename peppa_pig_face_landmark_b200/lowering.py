@@ -1023,6 +1023,34 @@ def _fuse_stem_block(pl):
     pl.ops[0:4] = [o]
 
 
+def _fuse_hm_partial(pl):
+    """Heat-map head: the decode (model.py:511-554 postp) needs only the maximum and first arg-max of every score map, so the
+    head conv's epilogue reduces each 128-pixel tile to (max, pixel index) per channel and the map itself is never stored
+    (436 MB per 256-face batch written and read back otherwise).  Split-head plans only (scores separate from offsets)."""
+    if os.environ.get("SKPS_HM_PART", "1") == "0":
+        return
+    for dec in pl.ops:
+        if dec.type != P.OP_HM_DECODE or len(dec.ins) < 2 or dec.ins[1] is None:
+            continue
+        hv = dec.ins[0]
+        prods = [o for o in pl.ops if o.type == P.OP_CONV and o.outs[0].buf is hv.buf]
+        readers = [o for o in pl.ops if o is not dec and any(i is not None and i.buf is hv.buf for i in o.ins)]
+        if len(prods) != 1 or readers or not (prods[0].flags & P.FLAG_TC) or (prods[0].flags & (P.FLAG_XF | P.FLAG_MMA)):
+            continue
+        hm = prods[0]
+        H, W = hv.H, hv.W
+        exact = (W % 128 == 0) if W >= 128 else (128 % W == 0 and H % (128 // W) == 0)
+        if hm.act != P.ACT_NONE or hm.ins[1] is not None or list(hm.s) != [1, 1] or not exact or hv.buf.C > 128:
+            continue
+        ldp = 128
+        pb = pl.new_buf(2 * ldp, (H * W) // 128, 1, P.DT_F32, hm.name + ":tile_max")
+        pv = P.View(pb, 0, 1, 2 * ldp)
+        hm.outs = [hm.outs[0], pv]
+        hm.flags |= P.FLAG_HM_PART
+        dec.ins = [dec.ins[0], dec.ins[1], pv]
+        dec.flags |= P.FLAG_HM_PART
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -1037,6 +1065,7 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
         _fuse_dw_pw(lw.plan)
         if input_u8:
             _fuse_stem_block(lw.plan)
+        _fuse_hm_partial(lw.plan)
     chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
     if chunk_env not in ("0", ""):
         lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)

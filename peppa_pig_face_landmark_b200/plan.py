@@ -106,6 +106,7 @@ FLAG_TC = 2           # conv runs on the tcgen05 path: w = hi matrix, w2 = lo ma
 FLAG_RES_FIRST = 4    # conv: act(conv + bias + residual) (ResNet/HRNet blocks) instead of act(conv + bias) + residual
 FLAG_MMA = 16         # 3x3 conv with few channels on the halo-tile mma.sync kernel (csrc/conv_mma.cu): w = packed fp16 hi/lo
 FLAG_XF = 32          # tensor-core 1x1 conv whose input is scaled by ins[2] = gate[n,c] inside the kernel (csrc/conv_xf.cu, XF_SCALE)
+FLAG_HM_PART = 64     # heat-map head conv writes per-tile (max, first arg-max) rows to outs[1] instead of the map; OP_HM_DECODE reads them from ins[2]
 FLAG_GAP_PARTIAL = 8  # depthwise conv also writes per-tile channel sums of its output to outs[1] ([tiles][C] per sample)
 DW_TILE_W = 16
 

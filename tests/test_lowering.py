@@ -144,7 +144,10 @@ def test_student_plan_fusions():
         assert se.ins[0].buf.H == -(-o.H // th) * -(-o.W // P.DW_TILE_W) and se.ints[3] == o.H * o.W
     dec = plan.ops[-1]
     hm = plan.ops[-2]
-    assert dec.type == P.OP_HM_DECODE and len(dec.ins) == 2 and dec.w.shape == (196, 128) and dec.ints[:2] == [98, 128]
+    assert dec.type == P.OP_HM_DECODE and len(dec.ins) == 3 and dec.w.shape == (196, 128) and dec.ints[:2] == [98, 128]
+    # the score maps are reduced to per-tile (max, arg-max) rows in the head conv's epilogue: 32 tiles of 128 pixels per face
+    assert (hm.flags & P.FLAG_HM_PART) and (dec.flags & P.FLAG_HM_PART) and hm.outs[1].buf is dec.ins[2].buf
+    assert (hm.outs[1].buf.H, hm.outs[1].buf.W, hm.outs[1].buf.C) == (32, 1, 256)
     assert hm.type == P.OP_CONV and hm.outs[0].buf.C == 104 and hm.ins[0].buf is dec.ins[1].buf
 
 
