@@ -148,13 +148,14 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 StemBlockW W;
                 memcpy(&W, e->h_weights.data() + op.w_off, sizeof(W));
                 StemBlockK k;
-                k.in = (const uint8_t*)in0.base;
+                k.in = e->f32_mode ? nullptr : (const uint8_t*)in0.base;
+                k.in_f32 = e->f32_mode ? (const float*)in0.base : nullptr;      // resolve() points at d_in_f32 in this mode
                 k.H = in0.H; k.W = in0.W; k.Hq = out0.H; k.Wq = out0.W;
                 k.img0 = 0; k.n_tiles = batch * (out0.H / 8) * (out0.W / 16);
                 k.dw1 = e->d_weights + op.i[0];
                 k.out = out0.base; k.out_fmt = out0.fmt; k.out_plane = out0.plane; k.out_ld = out0.ld; k.out_coff = out0.c_off;
-                if (e->f32_mode || in0.fmt != DT_U8 || !stem_block_supported(in0.H, in0.W, out0.C, out0)) {
-                    set_error("stem block: needs the uint8 input path and a supported shape");
+                if (in0.fmt != DT_U8 || !stem_block_supported(in0.H, in0.W, out0.C, out0)) {
+                    set_error("stem block: unsupported shape");
                     rc = 1;
                     break;
                 }

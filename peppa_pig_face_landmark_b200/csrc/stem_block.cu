@@ -109,13 +109,13 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
         const int sy0 = ey0 - 1, sx0 = ex0 - 1;               // half-res origin of the 19 x 35 stem window
         const int iy0 = 2 * sy0 - 1, ix0 = 2 * sx0 - 1;       // input origin of the 39 x 71 window
         // ---- S0: input window, /255 (true division, as numpy does), zero outside the crop (the stem's padding)
-        const uint8_t* src = p.in + (long long)img * p.H * p.W * 3;
         for (int i = tid; i < SB_NI; i += SB_THREADS) {
             const int r = i / SB_IW, c = i - r * SB_IW, y = iy0 + r, x = ix0 + c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                const uint8_t* px = src + ((long long)y * p.W + x) * 3;
-                v.x = lut[px[0]]; v.y = lut[px[1]]; v.z = lut[px[2]];
+                const long long o = (((long long)img * p.H + y) * p.W + x) * 3;
+                if (p.in_f32) { v.x = p.in_f32[o]; v.y = p.in_f32[o + 1]; v.z = p.in_f32[o + 2]; }
+                else { v.x = lut[p.in[o]]; v.y = lut[p.in[o + 1]]; v.z = lut[p.in[o + 2]]; }
             }
             *reinterpret_cast<float4*>(sA + 4 * i) = v;
         }

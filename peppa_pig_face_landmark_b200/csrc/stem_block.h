@@ -24,6 +24,7 @@ struct StemBlockW {
 
 struct StemBlockK {
     const uint8_t* in;         // [N][H][W][3] uint8
+    const float* in_f32;       // or [N][H][W][3] float32 already divided by 255 (ONNXEngine.__call__ feeds float32); null = uint8
     int H, W, Hq, Wq;          // input size, output (quarter-resolution) size
     int img0, n_tiles;         // first sample, tiles in this launch
     const float* dw1;          // device: [9][E] stride-2 depthwise weights then [E] bias
