@@ -59,8 +59,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float hm_sv[8][32];                 // heat-map head: per-warp column maxima, combined across the 4 lane quarters
-    __shared__ int hm_si[8][32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -225,6 +223,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                     argmax_scatter<16>(v, id, 16, lane); argmax_scatter<8>(v, id, 8, lane); argmax_scatter<4>(v, id, 4, lane);
                     argmax_scatter<2>(v, id, 2, lane); argmax_scatter<1>(v, id, 1, lane);
+                    // per-warp column maxima are combined across the 4 lane quarters through the (otherwise unused) store
+                    // staging area of the dynamic shared memory: [8 warps][32] float then [8][32] int
+                    float(*hm_sv)[32] = reinterpret_cast<float(*)[32]>(smem_raw + (stage_out - smem_u32(smem_raw)));
+                    int(*hm_si)[32] = reinterpret_cast<int(*)[32]>(smem_raw + (stage_out - smem_u32(smem_raw)) + 1024);
                     hm_sv[warp - 4][lane] = v[0];
                     hm_si[warp - 4][lane] = id[0];
                     asm volatile("bar.sync %0, 128;" ::"r"(1 + half_id) : "memory");
@@ -466,7 +468,7 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     // 16-byte aligned destination whose channel count is a multiple of 8 (the swizzle-free box clips at Cout).
     const int oes = s.out_fmt == DT_SPLIT16 ? 2 : 4;
     k.tma_store = (s.out_cstride == 1 && (s.Cout % 8) == 0 && ((size_t)s.out_ld * oes) % 16 == 0 &&
-                   ((size_t)s.out_coff * oes) % 16 == 0 && s.tma_store_hint != 1) ? 1 : 0;
+                   ((size_t)s.out_coff * oes) % 16 == 0 && s.tma_store_hint != 1 && !s.hm_val) ? 1 : 0;
     // two staging buffers per epilogue warp group when the pipeline still gets its stages, else one
     const size_t budget = 227 * 1024 - 1024 - 1024;                // minus static smem slack and alignment pad
     const int want_stages = (int)((budget - 2 * 16384) / stage_bytes) > MAX_STAGES ? MAX_STAGES
@@ -476,7 +478,7 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     int stages = (int)((budget - out_stage) / stage_bytes);
     k.stages = stages > MAX_STAGES ? MAX_STAGES : stages;
     SKPS_CHECK(k.stages >= 2, "conv_tc: tile too large for shared memory");
-    L.smem_bytes = (int)(k.stages * stage_bytes + out_stage + 1024);
+    L.smem_bytes = (int)(k.stages * stage_bytes + out_stage + 1024 + (s.hm_val ? 2048 : 0));    // + the arg-max exchange area
 
     // activations: (C, W, H, N) fp16, channel window [in_coff, in_coff+Cin) of rows of in_ld channels
     for (int plane = 0; plane < 2; ++plane) {
