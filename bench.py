@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the full-pipeline (configs 3/5) and detector legs")
+    ap.add_argument("--pipeline-streams", type=int, default=16)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -293,6 +295,21 @@ def main():
     h2d = B * 256 * 256 * 3
     d2h = B * (196 + 98) * 4
 
+    # ---- BASELINE configs 3 and 5: the whole FaceAna path (frame upload -> detector -> NMS -> crops -> landmarks ->
+    # temporal layer -> results on the host) for S concurrent video streams per GPU; streams shard across ranks with no
+    # data-path collective, under torchrun the result rows are collected with one NCCL all_gather per call
+    pipeline = None
+    if not args.no_pipeline:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_streams
+        pipeline = {}
+        for name in ("1080p_4faces", "4k_16faces"):
+            r = bench_streams.run_config(name, n_streams=args.pipeline_streams, batches=10, warmup=3, gather=world > 1,
+                                         dist=dist if world > 1 else None, rank=rank, world=world, length=4)
+            if r is not None:
+                pipeline[name] = r
+                log("pipeline %s: %.0f frames/s, %.0f faces/s" % (name, r["frames_per_s"], r["faces_per_s"]))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,6 +341,9 @@ def main():
 
     op_ms = [time_op(i, 5) for i in range(len(eng.plan.ops))]
     split = {}
+    if os.environ.get("SKPS_BENCH_OPS"):
+        for i, (op, t) in enumerate(zip(eng.plan.ops, op_ms)):
+            log("op %2d %-18s %7.1f us  %s" % (i, P.OP_NAMES[op.type], 1e3 * t, op.name[-60:]))
     for op, t in zip(eng.plan.ops, op_ms):
         kind = P.OP_NAMES[op.type] + ("/xf_scale" if op.flags & P.FLAG_XF else "/tc" if op.flags & P.FLAG_TC else "")
         split[kind] = split.get(kind, 0.0) + t
@@ -369,6 +389,12 @@ def main():
                 "whole_net_frac_of_split_ceiling": faces_per_s / world * STUDENT_FLOP_PER_FACE / 1e12 / (peak_tf / 3.0),
                 "whole_net_frac_readme_1.39G": faces_per_s / world * STUDENT_README_GFLOP / 1e12 / peak_tf}
 
+    detector = None
+    if not args.no_pipeline:
+        import bench_detector
+        detector = [bench_detector.run(b, n=30, peaks=(peak_tf, peak_hbm)) for b in (1, 16)]
+        log("detector: " + ", ".join("batch %d %.2f ms" % (d["batch"], d["ms"]) for d in detector))
+
     cpu = None
     if not args.no_cpu_baseline:
         log("cpu baseline on %d host threads" % host_cores())
@@ -388,6 +414,7 @@ def main():
                 "steps": e2e_steps, "api": "ONNXEngine.stream_u8 (pinned host crops in, host landmarks+scores out, 2 batches in flight: H2D of step i+1 overlaps compute of step i)"},
         "gpu_launches": lib.skps_engine_launches_for_batch(eng.handle, B) * args.steps,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "pipeline": pipeline, "detector": detector,
     }
     print(json.dumps(line))
     if world > 1:

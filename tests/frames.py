@@ -34,18 +34,34 @@ def canvas_640(img=None):
 
 
 def _background(h, w):
+    if (h, w) not in _BG_CACHE:
+        _BG_CACHE[(h, w)] = _background_make(h, w)
+    return _BG_CACHE[(h, w)].copy()
+
+
+_BG_CACHE = {}
+
+
+def _background_make(h, w):
     yy = (np.arange(h, dtype=np.int32)[:, None] * 40) // h
     xx = (np.arange(w, dtype=np.int32)[None, :] * 40) // w
     g = (94 + yy + xx).astype(np.uint8)
     return np.repeat(g[:, :, None], 3, axis=2).copy()
 
 
+_FACE_CACHE = {}
+
+
 def multi_face_frame(h, w, grid, face_w, jitter=(0, 0), img=None):
     """`grid`=(rows, cols) copies of test1.jpg scaled to `face_w` wide on a smooth
     grey gradient.  Config 3: (1080,1920,(2,2),440); config 5: (2160,3840,(4,4),600)."""
-    img = load_test1() if img is None else img
     fh = int(round(273 * face_w / 410))
-    face = _resize(img, face_w, fh)
+    if img is None:
+        if face_w not in _FACE_CACHE:                    # the scaled face is the slow part (pure-numpy bilinear)
+            _FACE_CACHE[face_w] = _resize(load_test1(), face_w, fh)
+        face = _FACE_CACHE[face_w]
+    else:
+        face = _resize(img, face_w, fh)
     frame = _background(h, w)
     rows, cols = grid
     for r in range(rows):

@@ -1,6 +1,7 @@
 """Detector (yolov5n-0.5-face @384x640) forward time on one GPU: python tools/bench_detector.py [batch ...]
 Device-resident letterboxed uint8 canvases -> (N,15120,16) rows; CUDA events on the engine's stream.
-Prints one JSON line per batch with the share of conv MACs routed to the tcgen05 kernel."""
+Prints one JSON line per batch with the share of conv MACs routed to the tcgen05 kernel and the roofline fractions
+(tensor: 2*MAC / time against the measured bf16 peak; HBM: the plan's per-op tensor bytes / time against the measured copy rate)."""
 import json
 import os
 import sys
@@ -9,12 +10,12 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
-import torch  # noqa: E402
-from peppa_pig_face_landmark_b200 import ONNXEngine, plan as P  # noqa: E402
 
-batches = [int(a) for a in sys.argv[1:]] or [1, 16]
-path = os.path.join(ROOT, "peppa_pig_face_landmark_b200", "pretrained", "yolov5n-0.5.onnx")
-for B in batches:
+
+def run(B, n=50, peaks=None):
+    import torch
+    from peppa_pig_face_landmark_b200 import ONNXEngine, plan as P
+    path = os.path.join(ROOT, "peppa_pig_face_landmark_b200", "pretrained", "yolov5n-0.5.onnx")
     eng = ONNXEngine(path, max_batch=B)
     tc = tot = 0
     for op in eng.plan.ops:
@@ -31,14 +32,23 @@ for B in batches:
             eng.forward_device(x, outs, s)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        n = 50
         for _ in range(n):
             eng.forward_device(x, outs, s)
         e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    print(json.dumps({"workload": "yolov5n-0.5-face 384x640 forward+decode", "batch": B, "ms": ms,
-                      "frames_per_s": B / ms * 1e3, "tc_mac_share": tc / tot, "launches": len(eng.plan.ops),
-                      "tflops_2mac": 2 * eng.plan.macs * B / ms / 1e9,
-                      "any_w": os.environ.get("SKPS_TC_ANY_W", "default")}))
+    bytes_per_frame = sum(eng.plan.bytes_per_sample(op) for op in eng.plan.ops)
+    r = {"workload": "yolov5n-0.5-face 384x640 forward+decode", "batch": B, "ms": ms,
+         "frames_per_s": B / ms * 1e3, "tc_mac_share": tc / tot, "launches": len(eng.plan.ops),
+         "tflops_2mac": 2 * eng.plan.macs * B / ms / 1e9, "gbs_plan_bytes": bytes_per_frame * B / ms / 1e6,
+         "plan_bytes_per_frame": bytes_per_frame, "mac_per_frame": int(eng.plan.macs)}
+    if peaks:
+        r["frac_tensor_peak"] = r["tflops_2mac"] / peaks[0]
+        r["frac_hbm_peak"] = r["gbs_plan_bytes"] / peaks[1]
     del eng
+    return r
+
+
+if __name__ == "__main__":
+    for B in [int(a) for a in sys.argv[1:]] or [1, 16]:
+        print(json.dumps(run(B)))

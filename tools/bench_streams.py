@@ -31,13 +31,13 @@ def make_streams(torch, frames, maker, n_streams, length=6, seed0=0, pin=True):
     return out
 
 
-def run_config(name, n_streams=16, batches=12, warmup=3, gather=False, dist=None, rank=0, world=1):
+def run_config(name, n_streams=16, batches=12, warmup=3, gather=False, dist=None, rank=0, world=1, length=6):
     """Returns a dict with whole-job frames/s and faces/s (all ranks), or None on ranks != 0."""
     import torch
     import frames
     from Skps import FaceAnaStreams
     maker, topk = getattr(frames, CONFIGS[name][0]), CONFIGS[name][1]
-    seqs = make_streams(torch, frames, maker, n_streams, seed0=1000 * rank)
+    seqs = make_streams(torch, frames, maker, n_streams, length=length, seed0=1000 * rank)
     H, W = seqs[0][0].shape[:2]
     fa = FaceAnaStreams(n_streams=n_streams, top_k=topk, max_frame_hw=(H, W))
     L = len(seqs[0])

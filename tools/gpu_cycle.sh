@@ -12,9 +12,10 @@ echo "== gpu suite" | tee -a $OUT/steps.log
 timeout 1200 python -m pytest tests -m gpu -q > $OUT/t_gpu.log 2>&1; echo "gpu suite rc=$?" | tee -a $OUT/steps.log
 tail -6 $OUT/t_gpu.log
 echo "== bench" | tee -a $OUT/steps.log
-timeout 600 python bench.py --steps 20 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/steps.log
+SKPS_BENCH_OPS=1 timeout 600 python bench.py --steps 20 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/steps.log
 python -c "
-import json; d=json.load(open('$OUT/bench.json')); r=d['roofline']; print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value']); print('dominant', r['kernel_ms'], r['achieved'], 'hbm', r['hbm_kernel']); print(r['op_class_ms'], r['op_sum_ms'])"
+import json; d=json.load(open('$OUT/bench.json')); r=d['roofline']; print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value']); print('dominant', r['kernel_ms'], r['achieved'], 'hbm', r['hbm_kernel']); print(r['op_class_ms'], r['op_sum_ms']); print('pipeline', {k: (round(v['frames_per_s']), round(v['faces_per_s'])) for k, v in (d.get('pipeline') or {}).items()}); print('detector', [(x['batch'], round(x['ms'], 3)) for x in (d.get('detector') or [])])"
+grep " op " $OUT/bench.err | sort -k6 -n -r | head -30
 tail -3 $OUT/bench.err
 echo "== launch list" | tee -a $OUT/steps.log
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/student_b256_launches.csv python tools/profile_student.py 256 1 student > $OUT/ncu_student.log 2>&1; echo "ncu student rc=$?" | tee -a $OUT/steps.log

@@ -34,8 +34,8 @@ def report(which="student", batch=2, out=sys.stdout):
     read = {}
     from peppa_pig_face_landmark_b200 import plan as P
     for op in eng.plan.ops:
-        outs = op.outs[1:] if (op.type == P.OP_CONV and op.flags & P.FLAG_HM_PART) else op.outs     # the heat map itself is not stored
-        for v in outs:
+        stored = op.outs[1:] if (op.type == P.OP_CONV and op.flags & P.FLAG_HM_PART) else op.outs     # the heat map itself is not stored
+        for v in stored:
             written[v.buf.idx] = max(written.get(v.buf.idx, 0), v.c_off + (v.C - 1) * v.c_stride + 1)
         for v in op.ins:
             if v is not None:
