@@ -110,6 +110,13 @@ SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W, int Cin, c
                                  float out_scale, const float* residual, int out_split, float* out, int stride,
                                  int res_first, int max_batch);
 
+/* Unit-test entry of the transposed heat-map head kernel (csrc/conv_hm.cu; kps graph /student/hm/Conv + the arg-max half of
+ * postp, TRAIN/face_landmark/lib/core/base_trainer/model.py:511-554): x float32 NHWC, w_hi/w_lo (n_tile, K_pad) float16 as
+ * packed by plan.pack_tc_weights -> per 256-pixel tile and channel the maximum score and its first pixel index (y*W+x):
+ * val / idx are [N][H*W/256][128] float32 / int32. */
+SKPS_API int skps_debug_conv_hm(const float* x, int N, int H, int W, int Cin, const void* w_hi, const void* w_lo,
+                                const float* bias, int Cout, int n_tile, float out_scale, float* val, int* idx);
+
 /* Debug/unit-test entry of the fused producer -> 1x1 conv kernels (csrc/conv_xf.cu): mode 0 = squeeze-excite scale
  * (x * gate[n,c]) ahead of the conv, mode 1 = depthwise 3x3 [over concat(bilinear_x2(low), x)] ahead of the conv.
  * Replaces, for one layer, what onnxruntime runs for the reference's ONNX nodes Mul->Conv / Resize->Concat->Conv(dw)->Conv

@@ -20,6 +20,7 @@ SOURCES = {
     "conv_simt.cu": [],
     "conv_tc.cu": [],
     "conv_xf.cu": [],
+    "conv_hm.cu": [],
     "stem_block.cu": [],
     "conv_mma.cu": [],
     "dw_tma.cu": [],

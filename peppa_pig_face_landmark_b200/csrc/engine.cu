@@ -13,6 +13,7 @@
 #include "../../include/skps_b200.h"
 #include "common.h"
 #include "conv_mma.h"
+#include "conv_hm.h"
 #include "conv_tc.h"
 #include "conv_xf.h"
 #include "dw_tma.h"
@@ -51,6 +52,7 @@ struct skps_engine {
     bool use_graph = true;
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
+    std::vector<HmLayer> hm;              // per op; valid for the heat-map head when its partial rows are 256-pixel tiles
     std::vector<ConvMmaLayer> mma;        // per op; valid where ops[i].flags & FLAG_MMA
     std::vector<XfLayer> xf;              // per op; fused producer -> pointwise conv layers (OP_DWPW, OP_CONV with FLAG_XF)
     std::vector<DwTmaLayer> dwt;          // per op; TMA-staged depthwise layers (valid flag)
@@ -116,6 +118,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                     break;
                 }
                 if (op.flags & FLAG_TC) {
+                    if (e->hm[i].valid) {
+                        rc = hm_launch(e->hm[i], batch, b0, e->num_sms, s);
+                        break;
+                    }
                     rc = tc_launch(e->tc[i], batch, b0, e->num_sms, s);
                     break;
                 }
@@ -289,6 +295,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
         }
     }
     e->tc.resize(n_ops);
+    e->hm.resize(n_ops);
     for (int i = 0; i < n_ops; ++i) {
         const OpDesc& op = e->ops[i];
         if (op.type != OP_CONV || !(op.flags & FLAG_TC) || (op.flags & FLAG_XF)) continue;
@@ -314,6 +321,17 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
             // out[1] = [tiles][2 * ld] per sample: ld maxima then ld arg-max indices; the map itself is not stored
             TView part = resolve(e, op.out[1]);
             s.hm_val = (float*)part.base; s.hm_idx = (int*)part.base + part.ld / 2; s.hm_ld = part.ld;
+            // the lowering sizes the partial buffer for 128-pixel tiles (conv_tc epilogue) or 256-pixel tiles (conv_hm.cu)
+            const int tile_px = part.H * part.W > 0 ? out0.H * out0.W / (part.H * part.W) : 0;
+            if (tile_px == HM_TILE_PIXELS) {
+                if (hm_prepare(e->hm[i], s)) {
+                    char tmp[900];
+                    snprintf(tmp, sizeof(tmp), "%s", get_error());
+                    set_error("op %d: %s", i, tmp);
+                    return fail("hm");
+                }
+                continue;
+            }
         }
         if (op.dh != op.dw || op.ph != op.pw || tc_prepare(e->tc[i], s)) {
             char tmp[900];

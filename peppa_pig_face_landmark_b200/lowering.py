@@ -1043,7 +1043,12 @@ def _fuse_hm_partial(pl):
         if hm.act != P.ACT_NONE or hm.ins[1] is not None or list(hm.s) != [1, 1] or not exact or hv.buf.C > 128:
             continue
         ldp = 128
-        pb = pl.new_buf(2 * ldp, (H * W) // 128, 1, P.DT_F32, hm.name + ":tile_max")
+        # 256-pixel row-block tiles run on the transposed head kernel (csrc/conv_hm.cu: channels on the TMEM lanes, the
+        # arg-max is a per-thread scan); other shapes keep conv_tc's 128-pixel tiles and its reduce-scatter epilogue
+        cin = hm.ins[0].C
+        wide = (os.environ.get("SKPS_HM_T", "1") != "0" and 8 <= W <= 256 and 256 % W == 0 and (H * W) % 256 == 0
+                and cin % 8 == 0 and cin <= 128 and hm.ints[1] == 1)
+        pb = pl.new_buf(2 * ldp, (H * W) // (256 if wide else 128), 1, P.DT_F32, hm.name + ":tile_max")
         pv = P.View(pb, 0, 1, 2 * ldp)
         hm.outs = [hm.outs[0], pv]
         hm.flags |= P.FLAG_HM_PART

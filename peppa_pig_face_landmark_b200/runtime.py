@@ -54,6 +54,8 @@ SIGNATURES = {
                                       C.c_int, C.c_int]),
     "skps_debug_conv_xf": (C.c_int, [C.c_int, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp,
                                      C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_float, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
+    "skps_debug_conv_hm": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_float,
+                                    c_vp, c_vp]),
     "skps_debug_se_fc": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp]),
     "skps_debug_hm_decode": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "skps_debug_conv_mma": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_int, C.c_int, c_vp, c_vp, C.c_int, C.c_float, c_vp,

@@ -172,3 +172,38 @@ def test_conv_tc_elementwise_error_bound_small_and_large_inputs(x_scale):
     worst = (err / bound).max()
     print("conv_tc element-wise error / bound at |x|~%g: %.3f" % (x_scale, worst))
     assert worst <= 1.0
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 64, 128, 104), (2, 32, 32, 128, 98), (5, 16, 16, 64, 24), (1, 8, 32, 72, 128)])
+def test_conv_hm_transposed_head_matches_fp64_argmax(shape):
+    """csrc/conv_hm.cu: score maps on the TMEM lanes, per-tile (max, first arg-max) from a per-thread scan.  Against an fp64
+    conv: the per-tile maximum within fp32 noise, and the reported pixel must BE a maximum of its tile (its fp64 score within
+    noise of the tile's fp64 maximum); exact ties (planted duplicates) must resolve to the first pixel."""
+    from peppa_pig_face_landmark_b200 import plan as P, runtime as rt
+    lib = rt.load_library()
+    N, H, W, Cin, Cout = shape
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((N, H, W, Cin)).astype(np.float32)
+    x[0, 1, 3] = x[0, 0, 5]                                  # duplicate pixels: equal scores in every map, first must win
+    x[0, 3 % H, 7] = x[0, 0, 5]
+    w = (rng.standard_normal((Cout, 1, 1, Cin)) / np.sqrt(Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    n_tile, n_tiles = P.tc_tiling(Cout)
+    assert n_tiles == 1
+    hi, lo, out_scale = P.pack_tc_weights(w, n_tile, n_tiles)
+    hi, lo = np.ascontiguousarray(hi), np.ascontiguousarray(lo)
+    tiles = H * W // 256
+    val = np.zeros((N, tiles, 128), np.float32)
+    idx = np.zeros((N, tiles, 128), np.int32)
+    rt.check(lib.skps_debug_conv_hm(x.ctypes.data, N, H, W, Cin, hi.ctypes.data, lo.ctypes.data, b.ctypes.data, Cout, n_tile,
+                                    out_scale, val.ctypes.data, idx.ctypes.data))
+    ref = (x.reshape(N, H * W, Cin).astype(np.float64) @ w.reshape(Cout, Cin).astype(np.float64).T + b).reshape(N, tiles, 256, Cout)
+    rmax = ref.max(axis=2)                                   # [N][tiles][Cout]
+    assert np.abs(val[..., :Cout] - rmax).max() < 2e-5 * (np.abs(ref).max() + 1)
+    loc = idx[..., :Cout] - (np.arange(tiles) * 256)[None, :, None]
+    assert loc.min() >= 0 and loc.max() < 256
+    picked = np.take_along_axis(ref, loc[:, :, None, :], axis=2)[:, :, 0, :]
+    assert np.abs(picked - rmax).max() < 2e-5 * (np.abs(ref).max() + 1)
+    # the duplicated pixel: wherever it is the tile maximum, the first copy (pixel 5 of tile 0) must be reported
+    dup = np.isclose(ref[0, 0, 5], rmax[0, 0], rtol=0, atol=1e-12)
+    assert (loc[0, 0][dup] == 5).all()
