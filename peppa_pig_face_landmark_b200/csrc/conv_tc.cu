@@ -247,6 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int acc = 0;
         uint32_t acc_phase = 0;
         int store_i = 0;                 // TMA stores issued by this warp group so far
+        int chunk_ctr = 0;               // 32-column chunks handed out so far (same sequence in both groups)
         const int tiles_x = (p.W + p.bw - 1) / p.bw;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int g_idx = tile / p.n_tiles, n_idx = tile - g_idx * p.n_tiles;
@@ -265,7 +266,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const long long pix = row_ok ? ((long long)img * p.H + y) * p.W + x : 0;
             const uint32_t t_addr = tmem_base + (uint32_t)acc * 256u + (uint32_t)u * 128u + ((uint32_t)(q * 32) << 16);
             const int co_tile = n_idx * p.n_tile;
-            for (int c0 = half_id * 32; c0 < p.n_tile && co_tile + c0 < p.Cout; c0 += 64) {
+            // 32-column chunks alternate between the two warp groups with a counter that runs on across tiles: layers with an
+            // odd number of chunks per tile (Cout 24, 72, 40 ...) would otherwise leave all / two thirds of the epilogue to
+            // group 0 (the epilogue, not HBM, bounds those layers)
+            const int n_chunks = (min(p.n_tile, p.Cout - co_tile) + 31) >> 5;
+            for (int ci = 0; ci < n_chunks; ++ci) {
+                if (((chunk_ctr + ci) & 1) != half_id) continue;
+                const int c0 = ci * 32;
                 float v[32];
                 tmem_ld32(t_addr + (uint32_t)c0, v);
                 const int co0 = co_tile + c0;
@@ -423,6 +430,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     }
                 }
             }
+            chunk_ctr += n_chunks;
           }
             tc_fence_before();
             __syncwarp();

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) elementwise_kernel(const EwK p) {
 #undef SRC
 
 
-// 4-channel vector variant of the kernels above (modes 2-6) for unit-stride, 16-byte aligned views.
+// 4-channel vector variant of the kernels above (modes 1-6) for unit-stride, 16-byte aligned views.
 __device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 y) {
     return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
 }
@@ -410,6 +410,10 @@ __global__ void __launch_bounds__(256) elementwise4_kernel(const EwK p) {
         float4 p10 = SRC4(((long long)y1 * p.W + x0) * p.in_ld), p11 = SRC4(((long long)y1 * p.W + x1) * p.in_ld);
         float4 top = f4_fma(hx, p00, f4_scale(lx, p01)), bot = f4_fma(hx, p10, f4_scale(lx, p11));
         v = f4_fma(hy, top, f4_scale(ly, bot));
+    } else if (MODE == 1) {
+        // Resize nearest, asymmetric, floor (the ASPP pooled branch broadcasts a 1x1 map)
+        const int iy = (int)(((long long)oy * p.H) / p.Ho), ix = (int)(((long long)ox * p.W) / p.Wo);
+        v = SRC4(((long long)iy * p.W + ix) * p.in_ld);
     } else {
         v = SRC4(((long long)oy * p.W + ox) * p.in_ld);
         if (MODE == 4) {
@@ -450,9 +454,9 @@ static EwK make_ew(const TView& in, const TView& out, int batch) {
 }
 
 #define LAUNCH_EW(MODE, k, s)                                                     \
-    if ((MODE) >= 2 && ew_vec_ok(k)) {                                            \
+    if ((MODE) >= 1 && ew_vec_ok(k)) {                                            \
         (k).total /= 4;                                                           \
-        elementwise4_kernel<(MODE) >= 2 ? (MODE) : 2><<<blocks_for((k).total, 256), 256, 0, s>>>(k);   \
+        elementwise4_kernel<(MODE) >= 1 ? (MODE) : 2><<<blocks_for((k).total, 256), 256, 0, s>>>(k);   \
     } else {                                                                      \
         elementwise_kernel<MODE><<<blocks_for((k).total, 256), 256, 0, s>>>(k);   \
     }                                                                             \

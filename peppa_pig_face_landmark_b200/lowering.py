@@ -1056,6 +1056,71 @@ def _fuse_hm_partial(pl):
         dec.flags |= P.FLAG_HM_PART
 
 
+def _fold_affine_into_producers(pl):
+    """BatchNormalization (+ReLU) applied to a Concat of conv outputs (the ASPP tail, model.py Decoder/ASPP: conv1|conv2|conv3|
+    pooled branch -> bn_act): a per-channel affine commutes with the channel concat, so it folds into every producing conv
+    (rows of W and the bias scaled, the ReLU becomes the conv's activation) and the pass over the 256-channel tensor
+    disappears.  A nearest-resize producer (the broadcast pooled branch, itself conv+ReLU) gets the affine on its 1x1 source
+    tensor instead."""
+    if os.environ.get("SKPS_FOLD_AFFINE", "1") == "0":
+        return
+    for a in list(pl.ops):
+        if a.type != P.OP_AFFINE_ACT or a.act not in (P.ACT_NONE, P.ACT_RELU):
+            continue
+        vin, vout = a.ins[0], a.outs[0]
+        if vin.c_off != 0 or vin.c_stride != 1 or vin.C != vin.buf.C or vout.c_off != 0 or vout.c_stride != 1 or vout.C != vout.buf.C:
+            continue
+        prods = [o for o in pl.ops if o is not a and any(v.buf is vin.buf for v in o.outs)]
+        if any(i is not None and i.buf is vin.buf for o in pl.ops if o is not a for i in o.ins) or vin.buf in [v.buf for v in pl.outputs]:
+            continue
+        covered = np.zeros(vin.C, np.int32)
+        ok = True
+        for o in prods:
+            v = o.outs[0]
+            if v.c_stride != 1 or len(o.outs) != 1:
+                ok = False
+                break
+            covered[v.c_off:v.c_off + v.C] += 1
+            if o.type == P.OP_CONV:
+                ok &= (o.act == P.ACT_NONE and (len(o.ins) < 2 or o.ins[1] is None) and (len(o.ins) < 3 or o.ins[2] is None)
+                       and not (o.flags & (P.FLAG_XF | P.FLAG_MMA | P.FLAG_HM_PART)) and getattr(o, "w_ref", None) is not None
+                       and o.w_ref.shape[0] == v.C)
+            elif o.type == P.OP_RESIZE_NEAREST:
+                src = o.ins[0]
+                ok &= src.H * src.W == 1 and src.c_off == 0 and src.c_stride == 1 and src.C == src.buf.C == v.C and \
+                    sum(1 for q in pl.ops for i in q.ins if i is not None and i.buf is src.buf) == 1
+            else:
+                ok = False
+        if not ok or not (covered == 1).all():
+            continue
+        inv, shift = a.w.astype(np.float32), a.b.astype(np.float32)
+        for o in prods:
+            v = o.outs[0]
+            sc, sh = inv[v.c_off:v.c_off + v.C], shift[v.c_off:v.c_off + v.C]
+            if o.type == P.OP_CONV:
+                w = (o.w_ref * sc[:, None, None, None]).astype(np.float32)
+                b = ((o.b[:v.C] if o.b is not None else np.zeros(v.C, np.float32)) * sc + sh).astype(np.float32)
+                o.w_ref = w
+                if o.flags & P.FLAG_TC:
+                    hi, lo, out_scale = P.pack_tc_weights(w, o.ints[0], o.ints[1])
+                    o.w, o.w2, o.floats = hi, lo, [out_scale] + list(o.floats[1:])
+                else:
+                    o.w = w
+                o.b = b
+                o.act = a.act
+            else:
+                src = o.ins[0]
+                pl.ops.insert(pl.ops.index(o), P.Op(P.OP_AFFINE_ACT, [src], [src], a.act, w=sc.copy(), b=sh.copy(),
+                                                     name=a.name + ":pooled"))
+                src.buf.name += ":folded_bn"       # no longer the ONNX tensor of that name
+        # the consumers of the normalised tensor read the concat buffer itself
+        vin.buf.dtype = vout.buf.dtype
+        vin.buf.name = vout.buf.name              # it now holds the normalised tensor (tools/layer_report.py compares by name)
+        for o in pl.ops:
+            o.ins = [P.View(vin.buf, i.c_off, i.c_stride, i.C) if (i is not None and i.buf is vout.buf) else i for i in o.ins]
+        pl.ops.remove(a)
+
+
 def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     """Build the plan for one of the reference's graphs at a fixed input size.  use_tc routes every
     eligible dense conv to the tcgen05 kernel (float16 hi/lo split, see csrc/conv_tc.cu)."""
@@ -1064,6 +1129,7 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
     lw.analyse()
     lw.emit()
     _fuse_upsample_concat_dw(lw.plan)
+    _fold_affine_into_producers(lw.plan)
     if os.environ.get("SKPS_SE_FUSE", "1") != "0":
         _fuse_se_chain(lw.plan)
     if use_tc:

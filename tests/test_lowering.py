@@ -145,9 +145,16 @@ def test_student_plan_fusions():
     dec = plan.ops[-1]
     hm = plan.ops[-2]
     assert dec.type == P.OP_HM_DECODE and len(dec.ins) == 3 and dec.w.shape == (196, 128) and dec.ints[:2] == [98, 128]
-    # the score maps are reduced to per-tile (max, arg-max) rows in the head conv's epilogue: 32 tiles of 128 pixels per face
+    # the score maps are reduced to per-tile (max, arg-max) rows in the head conv's epilogue: 16 row-block tiles of 256 pixels
+    # per face (the transposed head kernel, csrc/conv_hm.cu)
     assert (hm.flags & P.FLAG_HM_PART) and (dec.flags & P.FLAG_HM_PART) and hm.outs[1].buf is dec.ins[2].buf
-    assert (hm.outs[1].buf.H, hm.outs[1].buf.W, hm.outs[1].buf.C) == (32, 1, 256)
+    assert (hm.outs[1].buf.H, hm.outs[1].buf.W, hm.outs[1].buf.C) == (16, 1, 256)
+    # the ASPP tail's BatchNorm+ReLU over the 256-channel concat is folded into the four producers: the only affine op left
+    # works on the pooled branch's 64 x 1 x 1 tensor
+    aff = [o for o in plan.ops if o.type == P.OP_AFFINE_ACT]
+    assert len(aff) == 1 and aff[0].outs[0].H * aff[0].outs[0].W == 1 and aff[0].outs[0].C == 64
+    aspp = [o for o in plan.ops if o.type == P.OP_CONV and "/aspp/conv" in o.name]
+    assert len(aspp) == 3 and all(o.act == P.ACT_RELU and o.b is not None for o in aspp)
     assert hm.type == P.OP_CONV and hm.outs[0].buf.C == 104 and hm.ins[0].buf is dec.ins[1].buf
 
 
