@@ -186,6 +186,28 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
     }
     __syncthreads();
 
+    // uint8 input: the 39 x 71 window of the NEXT tile is fetched into registers (packed b | g << 8 | r << 16 | valid << 24,
+    // 5 pixels per thread) while the current tile is in its expansion / depthwise phases, so S0 never waits on HBM
+    // (the exposed load latency was 8.6 % of the stall samples, profiles/r2_ncu_top5_ops_stalls.txt)
+    constexpr int SB_PRE = (SB_NI + SB_THREADS - 1) / SB_THREADS;
+    uint32_t pre[SB_PRE];
+    auto prefetch = [&](int tl) {
+        const int il = tl / tiles_per_img, tt = tl - il * tiles_per_img;
+        const int y0 = 4 * ((tt / tiles_x) * SB_TH) - 5, x0 = 4 * ((tt % tiles_x) * SB_TW) - 5;      // = iy0, ix0 of that tile
+        const uint8_t* src = p.in + (long long)(il + p.img0) * p.H * p.W * 3;
+#pragma unroll
+        for (int k = 0; k < SB_PRE; ++k) {
+            const int i = tid + k * SB_THREADS;
+            const int r = i / SB_IW, c = i - r * SB_IW, y = y0 + r, x = x0 + c;
+            uint32_t v = 0;
+            if (i < SB_NI && y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                const uint8_t* q = src + ((long long)y * p.W + x) * 3;
+                v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | (1u << 24);
+            }
+            pre[k] = v;
+        }
+    };
+    if (!p.in_f32 && (int)blockIdx.x < p.n_tiles) prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int img_l = tile / tiles_per_img, t = tile - img_l * tiles_per_img, img = img_l + p.img0;
         const int oy0 = (t / tiles_x) * SB_TH, ox0 = (t % tiles_x) * SB_TW;     // quarter-res origin of the tile
@@ -193,15 +215,27 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
         const int sy0 = ey0 - 1, sx0 = ex0 - 1;               // half-res origin of the 19 x 35 stem window
         const int iy0 = 2 * sy0 - 1, ix0 = 2 * sx0 - 1;       // input origin of the 39 x 71 window
         // ---- S0: input window, /255 (true division, as numpy does), zero outside the crop (the stem's padding)
-        for (int i = tid; i < SB_NI; i += SB_THREADS) {
-            const int r = i / SB_IW, c = i - r * SB_IW, y = iy0 + r, x = ix0 + c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-                const long long o = (((long long)img * p.H + y) * p.W + x) * 3;
-                if (p.in_f32) { v.x = p.in_f32[o]; v.y = p.in_f32[o + 1]; v.z = p.in_f32[o + 2]; }
-                else { v.x = lut[p.in[o]]; v.y = lut[p.in[o + 1]]; v.z = lut[p.in[o + 2]]; }
+        if (p.in_f32) {
+            for (int i = tid; i < SB_NI; i += SB_THREADS) {
+                const int r = i / SB_IW, c = i - r * SB_IW, y = iy0 + r, x = ix0 + c;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                    const long long o = (((long long)img * p.H + y) * p.W + x) * 3;
+                    v.x = p.in_f32[o]; v.y = p.in_f32[o + 1]; v.z = p.in_f32[o + 2];
+                }
+                *reinterpret_cast<float4*>(sA + 4 * i) = v;
             }
-            *reinterpret_cast<float4*>(sA + 4 * i) = v;
+        } else {
+#pragma unroll
+            for (int k = 0; k < SB_PRE; ++k) {
+                const int i = tid + k * SB_THREADS;
+                if (i < SB_NI) {
+                    const uint32_t u = pre[k];
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (u >> 24) { v.x = lut[u & 255u]; v.y = lut[(u >> 8) & 255u]; v.z = lut[(u >> 16) & 255u]; }
+                    *reinterpret_cast<float4*>(sA + 4 * i) = v;
+                }
+            }
         }
         __syncthreads();
         // ---- S1: stem 3x3 stride 2 + h-swish over the 19 x 35 window; item = (pixel, 8 output channels)
@@ -312,6 +346,7 @@ stem_block_kernel(const StemBlockK p, const __grid_constant__ StemBlockW Wt) {
             tc_fence_after();
         }
         // ---- S4/S5 per 16-channel chunk of the expanded tensor: 1x1 16->E + ReLU into sB, then depthwise 3x3 s2 + ReLU
+        if (!p.in_f32 && tile + (int)gridDim.x < p.n_tiles) prefetch(tile + gridDim.x);     // in flight during S4 / S5
         const int y_ok0 = max(0, -ey0), y_ok1 = min(SB_EH, Hh - ey0), x_ok0 = max(0, -ex0), x_ok1 = min(SB_EW, Wh - ex0);
 #pragma unroll
         for (int ch = 0; ch < E / 16; ++ch) {
