@@ -835,7 +835,10 @@ struct SeFcK {
 // One CTA = 4 samples (they share every weight load), 1024 threads.  FC1 is split over `slices` thread groups that
 // each walk a strided share of the C inputs (8 independent weight loads in flight per thread), partials are reduced in
 // slice order; FC2: one thread per output channel.  (The first version -- 32 CTAs, one serial C-long loop per thread --
-// was pure L2 latency: 250 us per launch.)
+// was pure L2 latency: 250 us per launch.  A thread-block-cluster version - 8 CTAs x 32 samples, every CTA one eighth of
+// each FC's outputs, hidden units exchanged through distributed shared memory - was built and measured in round 2: correct,
+// but 250 us vs 170 us for the eight layers (1024-thread CTAs with 32 accumulators per thread cap at 64 registers and cannot
+// keep enough weight loads in flight), so this version stays.)
 __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const SeFcK p) {
     extern __shared__ __align__(16) float se_smem[];
     float4* mean = reinterpret_cast<float4*>(se_smem);                       // [C]       (x,y,z,w = the 4 samples)
@@ -894,116 +897,6 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const SeFcK p) {
     }
 }
 
-// ---- thread-block-cluster version (sm_90+: clusters + distributed shared memory) ------------------------------------------
-// The kernel above lets every CTA stream BOTH weight matrices (1.8 MB for the 960-channel blocks) through one SM to serve 4
-// samples: 25-37 us per launch, L2->SM latency/bandwidth bound, for 0.06 GFLOP.  Here a cluster of 8 CTAs serves 32 samples
-// and every CTA owns one eighth of each FC's OUTPUTS for all 32 samples:
-//   mean[C][32] (each CTA, redundantly)  ->  FC1 slice: Cr/8 hidden units  ->  slice broadcast into the 7 peers' shared
-//   memory (st.shared::cluster)  ->  cluster barrier  ->  FC2 slice: C/8 gate channels  ->  global.
-// Per CTA 1/8 of the weight bytes, every weight load is one coalesced 128-byte line used for 32 samples x 32 lanes, and the K
-// loops are split over the 32 warps so a thread makes ~30 dependent-latency round trips instead of 240.
-constexpr int SEC_CL = 8, SEC_SPC = 32;
-__device__ __forceinline__ uint32_t sec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __cluster_dims__(SEC_CL, 1, 1) __launch_bounds__(SE_THREADS) se_fc_cluster_kernel(const SeFcK p) {
-    extern __shared__ __align__(16) float sec_smem[];
-    float* big = sec_smem;                                   // [max(C,1024)][32]: the means, later the partial sums of a slice
-    float* hid = sec_smem + (size_t)(p.C > 1024 ? p.C : 1024) * SEC_SPC;      // [Cr][32] all hidden units (filled by the cluster)
-    uint32_t rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n0 = (blockIdx.x / SEC_CL) * SEC_SPC;
-    // ---- channel means of the cluster's 32 samples: consecutive threads read consecutive channels; the quad index of the
-    // sample is XOR-swizzled with the channel so that these column writes spread over the banks
-    for (int i = tid; i < p.C * SEC_SPC; i += SE_THREADS) {
-        const int m = i / p.C, c = i - m * p.C;
-        float sum = 0.f;
-        if (n0 + m < p.batch) {
-            const float* src = p.part + (long long)(n0 + m) * p.tiles * p.part_ld + p.part_coff + c;
-            for (int t = 0; t < p.tiles; ++t) sum += src[(long long)t * p.part_ld];
-        }
-        big[c * SEC_SPC + ((((m >> 2) ^ (c & 7)) << 2) | (m & 3))] = sum / p.hw;
-    }
-    __syncthreads();
-    // ---- FC1: hidden units [rank*Jp, rank*Jp + Jp); lane = hidden unit, warp = slice of the channels
-    const int Jp = (p.Cr + SEC_CL - 1) / SEC_CL;             // <= 32
-    float acc[SEC_SPC];
-#pragma unroll
-    for (int m = 0; m < SEC_SPC; ++m) acc[m] = 0.f;
-    {
-        const int j = rank * Jp + lane;
-        const bool act = lane < Jp && j < p.Cr;
-        const float* wcol = p.w1t + (act ? j : 0);
-#pragma unroll 4
-        for (int c = warp; c < p.C; c += SE_THREADS / 32) {
-            const float w = act ? __ldg(wcol + (long long)c * p.Cr) : 0.f;
-            const float4* row = reinterpret_cast<const float4*>(big + c * SEC_SPC);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 a = row[q ^ (c & 7)];           // samples 4q .. 4q+3 (warp-wide broadcast)
-                acc[4 * q] = fmaf(a.x, w, acc[4 * q]); acc[4 * q + 1] = fmaf(a.y, w, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(a.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a.w, w, acc[4 * q + 3]);
-            }
-        }
-    }
-    __syncthreads();                                         // everyone is done reading the means: reuse `big` for partials
-#pragma unroll
-    for (int m = 0; m < SEC_SPC; ++m) big[(warp * 32 + lane) * SEC_SPC + (m ^ lane)] = acc[m];      // [slice][unit][sample^unit]
-    __syncthreads();
-    {
-        // thread = (hidden unit jl, sample m): sum the 32 slices in order, bias, activation, and broadcast to the cluster
-        const int jl = tid >> 5, m = tid & 31, j = rank * Jp + jl;
-        if (jl < Jp && j < p.Cr) {
-            float t = p.b1 ? p.b1[j] : 0.f;
-            for (int sl = 0; sl < SE_THREADS / 32; ++sl) t += big[(sl * 32 + jl) * SEC_SPC + (m ^ jl)];
-            t = apply_act(t, p.act1);
-            const uint32_t local = sec_smem_u32(hid + j * SEC_SPC + m);
-#pragma unroll
-            for (uint32_t r = 0; r < SEC_CL; ++r) {
-                uint32_t remote;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
-                asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(t) : "memory");
-            }
-        }
-    }
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    // ---- FC2: gate channels [rank*Ip, rank*Ip + Ip); lane + 32*(warp % 4) = channel slot, warp / 4 = slice of the hidden units
-    const int Ip = (p.C + SEC_CL - 1) / SEC_CL;              // <= 128
-    const int il = (warp & 3) * 32 + lane, sl2 = warp >> 2, i = rank * Ip + il;
-    const bool act2 = il < Ip && i < p.C;
-#pragma unroll
-    for (int m = 0; m < SEC_SPC; ++m) acc[m] = 0.f;
-    {
-        const float* wcol = p.w2t + (act2 ? i : 0);
-#pragma unroll 4
-        for (int j = sl2; j < p.Cr; j += SE_THREADS / 128) {
-            const float w = act2 ? __ldg(wcol + (long long)j * p.C) : 0.f;
-            const float4* row = reinterpret_cast<const float4*>(hid + j * SEC_SPC);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 a = row[q];
-                acc[4 * q] = fmaf(a.x, w, acc[4 * q]); acc[4 * q + 1] = fmaf(a.y, w, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(a.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(a.w, w, acc[4 * q + 3]);
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < SEC_SPC; ++m) big[(sl2 * 128 + il) * SEC_SPC + (m ^ lane)] = acc[m];       // [slice][slot][sample^lane]
-    __syncthreads();
-    for (int o = tid; o < Ip * SEC_SPC; o += SE_THREADS) {
-        const int m = o / Ip, l = o - m * Ip, ch = rank * Ip + l;       // consecutive threads -> consecutive channels of a sample
-        if (ch < p.C && n0 + m < p.batch) {
-            float t = p.b2 ? p.b2[ch] : 0.f;
-#pragma unroll
-            for (int sl = 0; sl < SE_THREADS / 128; ++sl) t += big[(sl * 128 + l) * SEC_SPC + (m ^ (l & 31))];
-            p.gate[(long long)(n0 + m) * p.gate_ld + p.gate_coff + ch] = apply_act(t, p.act2);
-        }
-    }
-    // no CTA may exit while a peer could still be writing its shared memory: all remote stores precede the barrier above
-}
-
 int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const float* b1, const float* w2t, const float* b2,
                  int Cr, int act1, int act2, int hw, int batch, cudaStream_t s) {
     SKPS_CHECK(part.fmt == DT_F32 && gate.fmt == DT_F32 && part.c_stride == 1 && gate.c_stride == 1 && part.C == gate.C &&
@@ -1022,21 +915,6 @@ int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const f
     if (!attr_set) {
         SKPS_CUDA(cudaFuncSetAttribute(se_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
-    }
-    {
-        static int use_cluster = -1;
-        if (use_cluster < 0) {
-            const char* e = getenv("SKPS_SE_CLUSTER");
-            use_cluster = (e && e[0] == '0') ? 0 : 1;
-            if (use_cluster) SKPS_CUDA(cudaFuncSetAttribute(se_fc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        }
-        const size_t csmem = ((size_t)(k.C > 1024 ? k.C : 1024) + (size_t)k.Cr) * SEC_SPC * sizeof(float);
-        if (use_cluster && k.Cr <= 32 * SEC_CL && k.C <= 128 * SEC_CL && csmem <= 200 * 1024) {
-            const int clusters = (batch + SEC_SPC - 1) / SEC_SPC;
-            se_fc_cluster_kernel<<<clusters * SEC_CL, SE_THREADS, csmem, s>>>(k);
-            SKPS_CUDA(cudaGetLastError());
-            return 0;
-        }
     }
     SKPS_CHECK(smem <= 96 * 1024, "se_fc: %d + %d channels do not fit shared memory", k.C, k.Cr);
     se_fc_kernel<<<(batch + SE_SAMPLES - 1) / SE_SAMPLES, SE_THREADS, smem, s>>>(k);

@@ -154,3 +154,35 @@ def test_student_128_cuda_matches_oracle(tmp_path):
     for i in range(5):
         o, k = sess.run(crops[i].transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))
         assert np.abs(xy[i] - o.reshape(-1)).max() * 128 < 1e-3 and np.abs(sc[i] - k.reshape(-1)).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_student_192_cuda_matches_oracle(tmp_path):
+    """A size the 128-pixel row-block tiling does not divide (48-, 24-, 12-wide maps): ragged tensor-core tiles, the fused
+    kernels' overhanging tiles and the pixels-on-lanes heat-map epilogue (48 x 48 maps are not whole 256-pixel row blocks)."""
+    import frames
+    from peppa_pig_face_landmark_b200 import ONNXEngine, graph_tools, lowering
+    from oracle.onnx_exec import Session
+    from oracle.host_ref import resize_linear_u8
+    src = os.path.join(os.path.dirname(lowering.__file__), "pretrained", "kps_student.onnx")
+    s192 = graph_tools.retarget_input_size(src, str(tmp_path / "s192.onnx"), 192)
+    crops = np.stack([resize_linear_u8(c, 192, 192) for c in frames.crop_variants(3)])
+    xy, sc = ONNXEngine(s192, max_batch=3).run_u8(crops)
+    sess = Session(s192)
+    for i in range(3):
+        o, k = sess.run(crops[i].transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))
+        assert np.abs(xy[i] - o.reshape(-1)).max() * 192 < 1e-3 and np.abs(sc[i] - k.reshape(-1)).max() < 1e-4
+
+
+@pytest.mark.gpu
+def test_teacher_128_cuda_matches_fp64_oracle(tmp_path):
+    """README's Teacher@128 variant on the GPU: 32 x 32 ... 4 x 4 branch maps (multi-image tiles)."""
+    from peppa_pig_face_landmark_b200 import ONNXEngine, teacher_graph as T
+    t128 = str(tmp_path / "t128.onnx")
+    T.build_teacher_onnx(t128, size=128)
+    crops = T.synthetic_crops(3, 128, 5)
+    xy, sc = ONNXEngine(t128, max_batch=4).run_u8(crops)
+    rxy, rsc = _oracle64(t128, crops)
+    dpx, dsc = np.abs(xy - rxy).max() * 128, np.abs(sc - rsc).max()
+    print("teacher@128 cuda vs fp64 oracle: %.2e px, %.2e score" % (dpx, dsc))
+    assert dpx < TOL_PX_TC and dsc < TOL_SCORE_TC
