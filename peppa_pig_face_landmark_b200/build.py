@@ -21,6 +21,7 @@ SOURCES = {
     "conv_tc.cu": [],
     "conv_xf.cu": [],
     "conv_hm.cu": [],
+    "conv_tct.cu": [],
     "stem_block.cu": [],
     "conv_mma.cu": [],
     "dw_tma.cu": [],

@@ -31,6 +31,7 @@
 #include "../../include/skps_b200.h"
 #include "common.h"
 #include "conv_tc.h"
+#include "conv_tct.h"
 #include "tc_ptx.h"
 
 namespace skps {
@@ -768,12 +769,26 @@ extern "C" SKPS_API int skps_debug_conv_tc2(const float* x, int N, int H, int W,
     s.out = out_split ? (void*)d_osplit : (void*)d_out; s.out_fmt = out_split ? DT_SPLIT16 : DT_F32;
     s.out_plane = cout_cap; s.out_ld = Cout; s.out_coff = 0; s.out_cstride = 1;
     s.res = d_res; s.res_fmt = DT_F32; s.res_plane = 0; s.res_ld = Cout; s.res_coff = 0;
-    TcLayer L;
-    if (tc_prepare(L, s)) return 1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (tct_applicable(s)) {                        // the engine routes such layers to the transposed kernel (conv_tct.cu)
+        float* d_zero = nullptr;
+        if (!s.bias) {
+            SKPS_CUDA(cudaMalloc(&d_zero, 1024 * 4));
+            SKPS_CUDA(cudaMemset(d_zero, 0, 1024 * 4));
+            s.bias = d_zero;
+        }
+        TctLayer T;
+        if (tct_prepare(T, s)) return 1;
+        if (tct_launch(T, N, 0, sms, 0)) return 1;
+        SKPS_CUDA(cudaDeviceSynchronize());
+        if (d_zero) cudaFree(d_zero);
+    } else {
+    TcLayer L;
+    if (tc_prepare(L, s)) return 1;
     if (tc_launch(L, N, 0, sms, 0)) return 1;
+    }
     SKPS_CUDA(cudaDeviceSynchronize());
     if (out_split) {
         // recombine hi+lo on the host side of the test

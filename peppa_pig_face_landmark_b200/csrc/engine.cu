@@ -15,6 +15,7 @@
 #include "conv_mma.h"
 #include "conv_hm.h"
 #include "conv_tc.h"
+#include "conv_tct.h"
 #include "conv_xf.h"
 #include "dw_tma.h"
 #include "stem_block.h"
@@ -52,6 +53,7 @@ struct skps_engine {
     bool use_graph = true;
     int num_sms = 148;
     std::vector<TcLayer> tc;              // per op; valid where ops[i].flags & FLAG_TC
+    std::vector<TctLayer> tct;            // per op; valid where the transposed kernel (conv_tct.cu) takes the layer
     std::vector<HmLayer> hm;              // per op; valid for the heat-map head when its partial rows are 256-pixel tiles
     std::vector<ConvMmaLayer> mma;        // per op; valid where ops[i].flags & FLAG_MMA
     std::vector<XfLayer> xf;              // per op; fused producer -> pointwise conv layers (OP_DWPW, OP_CONV with FLAG_XF)
@@ -120,6 +122,10 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
                 if (op.flags & FLAG_TC) {
                     if (e->hm[i].valid) {
                         rc = hm_launch(e->hm[i], batch, b0, e->num_sms, s);
+                        break;
+                    }
+                    if (e->tct[i].valid) {
+                        rc = tct_launch(e->tct[i], batch, b0, e->num_sms, s);
                         break;
                     }
                     rc = tc_launch(e->tc[i], batch, b0, e->num_sms, s);
@@ -296,6 +302,7 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
     }
     e->tc.resize(n_ops);
     e->hm.resize(n_ops);
+    e->tct.resize(n_ops);
     for (int i = 0; i < n_ops; ++i) {
         const OpDesc& op = e->ops[i];
         if (op.type != OP_CONV || !(op.flags & FLAG_TC) || (op.flags & FLAG_XF)) continue;
@@ -332,6 +339,15 @@ extern "C" SKPS_API int skps_engine_create(const int32_t* words, size_t n_words,
                 }
                 continue;
             }
+        }
+        if (op.dh == op.dw && op.ph == op.pw && tct_applicable(s)) {
+            if (tct_prepare(e->tct[i], s)) {
+                char tmp[900];
+                snprintf(tmp, sizeof(tmp), "%s", get_error());
+                set_error("op %d: %s", i, tmp);
+                return fail("tct");
+            }
+            continue;
         }
         if (op.dh != op.dw || op.ph != op.pw || tc_prepare(e->tc[i], s)) {
             char tmp[900];

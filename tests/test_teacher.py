@@ -180,9 +180,19 @@ def test_teacher_128_cuda_matches_fp64_oracle(tmp_path):
     from peppa_pig_face_landmark_b200 import ONNXEngine, teacher_graph as T
     t128 = str(tmp_path / "t128.onnx")
     T.build_teacher_onnx(t128, size=128)
+    import torch
+    from oracle.onnx_exec import Session
     crops = T.synthetic_crops(3, 128, 5)
     xy, sc = ONNXEngine(t128, max_batch=4).run_u8(crops)
     rxy, rsc = _oracle64(t128, crops)
-    dpx, dsc = np.abs(xy - rxy).max() * 128, np.abs(sc - rsc).max()
-    print("teacher@128 cuda vs fp64 oracle: %.2e px, %.2e score" % (dpx, dsc))
+    # The random-weight heat maps have near-tied maxima (landmark 35 of crop 0: 3.06885 at (23, 8) vs 3.06864 at (31, 18)); an
+    # arg-max flip there is a 44 px jump that the oracle's own float32 run makes too.  Such landmarks (fp32 and fp64 oracle
+    # more than a pixel apart) are ill-conditioned and are compared with the fp32 oracle, the others with fp64.
+    s32 = Session(t128, dtype=torch.float32)
+    xy32 = np.array([s32.run(c.transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))[0].reshape(-1) for c in crops])
+    tie = np.repeat((np.abs(xy32 - rxy).reshape(len(crops), -1, 2).max(-1) * 128 > 1.0), 2, axis=1)
+    assert tie.mean() < 0.05
+    ref = np.where(tie, xy32, rxy)
+    dpx, dsc = np.abs(xy - ref).max() * 128, np.abs(sc - rsc).max()
+    print("teacher@128 cuda vs oracle: %.2e px, %.2e score (%d near-tied landmark coordinates vs the fp32 oracle)" % (dpx, dsc, int(tie.sum())))
     assert dpx < TOL_PX_TC and dsc < TOL_SCORE_TC
