@@ -14,6 +14,12 @@
 // and 32 pixels per tcgen05.ld; bias / activation / fp16 hi-lo split, then the 32 x 32 block is written TRANSPOSED into the
 // warp's 4 KB staging slice (one 64-byte pixel row per store instruction, lane = channel) and leaves as one TMA store per
 // plane, so the NHWC layout of the output is unchanged.
+//
+// Halo-row stages (k3, 3x3 / dilation 1 / W in {32, 64}): as in conv_tc's opt-in mode a stage is (kx, 32-channel half): ONE
+// (bh+2)-row activation box (64-byte swizzled rows) serves the three ky taps - the B operand of tap ky is the 256 box rows that
+// start ky image rows in, a descriptor offset of ky * W * 64 bytes - next to the three ky weight tiles.  L2->SM bytes per tile
+// drop by a third (1728 -> 1152 KB at Cin = 128).  Opt-in (SKPS_TCT_K3=1): measured slower than the per-tap stages, see
+// tct_prepare.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <math.h>
@@ -83,6 +89,26 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constan
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int img_l = tile / p.tiles_per_img, t = tile - img_l * p.tiles_per_img;
                 const int y0 = t * p.bh;
+                if (p.k3) {
+                    const int halves = p.Cin >> 5, K_row = p.cchunks * 64;
+                    const uint32_t stage_bytes = 6u * 8192u + 2u * (uint32_t)p.xb;
+                    for (int kb = 0; kb < 3 * halves; ++kb) {
+                        const int kx = kb / halves, h = kb - kx * halves;
+                        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                        const uint32_t fb = smem_u32(&full_bar[stage]);
+                        mbar_expect_tx(fb, stage_bytes);
+                        const uint32_t ss = base + (uint32_t)stage * TCT_STAGE;
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const int kcol = (ky * 3 + kx) * K_row + h * 32;
+                            tma_load_2d(ss + (uint32_t)(2 * ky) * 8192u, &tmW_hi, fb, kcol, 0);
+                            tma_load_2d(ss + (uint32_t)(2 * ky + 1) * 8192u, &tmW_lo, fb, kcol, 0);
+                        }
+                        tma_load_4d(ss + 49152u, &tmX_hi, fb, h * 32, kx - 1, y0 - 1, img_l + p.img0);
+                        tma_load_4d(ss + 49152u + (uint32_t)p.xb, &tmX_lo, fb, h * 32, kx - 1, y0 - 1, img_l + p.img0);
+                        if (++stage == TCT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < kblocks; ++kb) {
                     const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
                     const int ky = tap / p.kw, kx = tap - ky * p.kw;
@@ -112,6 +138,29 @@ conv_tct_kernel(const __grid_constant__ CUtensorMap tmX_hi, const __grid_constan
                 mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * (uint32_t)TCT_N;
+                if (p.k3) {
+                    const int nkb = 3 * (p.Cin >> 5);
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait(smem_u32(&full_bar[stage]), phase);
+                        tc_fence_after();
+                        const uint32_t ss = base + (uint32_t)stage * TCT_STAGE;
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const uint64_t w_hi = make_smem_desc_sw64(ss + (uint32_t)(2 * ky) * 8192u);
+                            const uint64_t w_lo = make_smem_desc_sw64(ss + (uint32_t)(2 * ky + 1) * 8192u);
+                            // tap row ky: the 256 box rows that start ky image rows in
+                            const uint32_t xo = ss + 49152u + (uint32_t)(ky * p.W * 64);
+                            const uint64_t x_hi = make_smem_desc_sw64(xo), x_lo = make_smem_desc_sw64(xo + (uint32_t)p.xb);
+                            for (int k = 0; k < 2; ++k) {
+                                const uint64_t koff = (uint64_t)(k * 2);
+                                umma_f16(d_tmem, w_lo + koff, x_hi + koff, idesc, (kb | ky | k) != 0);
+                                umma_f16(d_tmem, w_hi + koff, x_lo + koff, idesc, 1u);
+                                umma_f16(d_tmem, w_hi + koff, x_hi + koff, idesc, 1u);
+                            }
+                        }
+                        umma_commit(smem_u32(&empty_bar[stage]));
+                        if (++stage == TCT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                } else
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
@@ -239,27 +288,38 @@ int tct_prepare(TctLayer& L, const TcSetup& s) {
     SKPS_CHECK(s.bias, "conv_tct: bias required");
     k.bias = s.bias;
     L.smem_bytes = TCT_STAGES * TCT_STAGE + 8 * 4096 + 1024;
+    {
+        // opt-in: measured on B200 the halo-row stages are SLOWER here (conv2 0.706 vs 0.649 ms) as they were in conv_tc
+        // (no gain) - both times the 64-byte-row operand layout is the common factor, so the third fewer L2->SM bytes do
+        // not pay for it.  Kept (and unit-tested with SKPS_TCT_K3=1) as the starting point for a 128-byte-row variant.
+        const char* e = getenv("SKPS_TCT_K3");
+        const int k3_on = (e && e[0] == '1') ? 1 : 0;
+        k.xb = (k.bh + 2) * s.W * 64;
+        k.k3 = (k3_on && s.kh == 3 && s.dil == 1 && (s.W == 32 || s.W == 64) && s.Cin % 32 == 0 &&
+                6 * 8192 + 2 * k.xb <= TCT_STAGE) ? 1 : 0;
+    }
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)s.Cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)s.in_ld * 2, (cuuint64_t)s.W * s.in_ld * 2, (cuuint64_t)s.H * s.W * s.in_ld * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)s.W, (cuuint32_t)k.bh, 1};
+        if (k.k3) { box[0] = 32; box[2] = (cuuint32_t)(k.bh + 2); }
         cuuint32_t estr[4] = {1, 1, 1, 1};
         void* base = (void*)((__half*)s.in_base + (plane ? s.in_plane : 0) + s.in_coff);
         CUresult r = enc(plane ? &L.x_lo : &L.x_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k.k3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tct X) failed: %d", (int)r);
     }
     const int K_pad = k.taps * k.cchunks * 64;
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[2] = {(cuuint64_t)K_pad, (cuuint64_t)s.n_tile};        // rows beyond n_tile: OOB zero fill
         cuuint64_t strides[1] = {(cuuint64_t)K_pad * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)TCT_M};
+        cuuint32_t box[2] = {(cuuint32_t)(k.k3 ? 32 : 64), (cuuint32_t)TCT_M};
         cuuint32_t estr[2] = {1, 1};
         void* base = (void*)(plane ? s.w_lo : s.w_hi);
         CUresult r = enc(plane ? &L.w_lo : &L.w_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, k.k3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SKPS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(tct W) failed: %d", (int)r);
     }
     // output: one box per epilogue warp and 32-pixel block: 32 channels x 32 consecutive pixels of a row, plain 64-byte rows

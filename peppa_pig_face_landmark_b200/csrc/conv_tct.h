@@ -11,6 +11,8 @@ namespace skps {
 struct TctK {                    // kernel parameters
     int W, bh, tiles_per_img, m_tiles, img0;    // tile = bh whole rows = 256 pixels
     int taps, kw, dil, pad, cchunks, Cin, Cout, act;
+    int k3;                      // halo-row stages: (kx, 32-channel half) = one (bh+2)-row box + the three ky weight tiles
+    int xb;                      // k3: bytes of one plane of the activation box
     float out_scale;             // exact power of two undoing the weight pre-scale
     const float* bias;
 };

@@ -79,12 +79,20 @@ def test_conv_tc_halo_row_mode(cfg, monkeypatch):
 
 @pytest.mark.parametrize("cfg", [
     # transposed kernel (csrc/conv_tct.cu): channels on the TMEM lanes, 256 pixels as N; split-fp16 output, no residual
-    (2, 64, 64, 128, 128, 3, 1, 1),      # decoder conv2
+    (2, 64, 64, 128, 128, 3, 1, 1),      # decoder conv2 (halo-row stages: 6-row boxes)
+    (2, 32, 32, 96, 128, 3, 1, 1),       # halo-row stages with 10-row boxes, three 32-channel halves
     (1, 32, 32, 64, 96, 3, 2, 0),        # dilated, 8-row tiles, Cout < 128 (the last lane quarter is clipped by the store)
     (3, 8, 128, 72, 104, 3, 1, 2),       # two-row tiles, K tail (72 channels), ragged Cout
     (2, 16, 256, 64, 128, 5, 1, 1),      # 5x5, one row per tile
 ])
 def test_conv_tct_transposed_kernel(cfg):
+    err = _run(*cfg, out_split=True)
+    assert err < 1e-5, (cfg, err)
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 128, 128, 3, 1, 1), (2, 32, 32, 96, 128, 3, 1, 1)])
+def test_conv_tct_halo_row_stages(cfg, monkeypatch):
+    monkeypatch.setenv("SKPS_TCT_K3", "1")             # opt-in stage layout (read by tct_prepare at every layer setup)
     err = _run(*cfg, out_split=True)
     assert err < 1e-5, (cfg, err)
 
