@@ -184,15 +184,26 @@ def test_teacher_128_cuda_matches_fp64_oracle(tmp_path):
     from oracle.onnx_exec import Session
     crops = T.synthetic_crops(3, 128, 5)
     xy, sc = ONNXEngine(t128, max_batch=4).run_u8(crops)
-    rxy, rsc = _oracle64(t128, crops)
     # The random-weight heat maps have near-tied maxima (landmark 35 of crop 0: 3.06885 at (23, 8) vs 3.06864 at (31, 18)); an
-    # arg-max flip there is a 44 px jump that the oracle's own float32 run makes too.  Such landmarks (fp32 and fp64 oracle
-    # more than a pixel apart) are ill-conditioned and are compared with the fp32 oracle, the others with fp64.
-    s32 = Session(t128, dtype=torch.float32)
-    xy32 = np.array([s32.run(c.transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))[0].reshape(-1) for c in crops])
-    tie = np.repeat((np.abs(xy32 - rxy).reshape(len(crops), -1, 2).max(-1) * 128 > 1.0), 2, axis=1)
+    # arg-max flip there is a 44 px jump that even the oracle's own float32 run makes on some hosts.  A landmark whose fp64
+    # map has a second peak (outside the 5x5 neighbourhood of the first) within 1e-3 relative of the maximum is
+    # ill-conditioned and left out of the coordinate comparison; its score still has to match.
+    s64 = Session(t128, dtype=torch.float64)
+    rxy, rsc, tie = [], [], []
+    for c in crops:
+        outs, kept = s64.run(c.transpose(2, 0, 1)[None].astype(np.float64) / 255.0, keep="all")
+        rxy.append(outs[0].reshape(-1)); rsc.append(outs[1].reshape(-1))
+        hm = [v for v in kept.values() if hasattr(v, "ndim") and v.ndim == 4 and v.shape[1] == 294][-1][0, :98].numpy()
+        t = np.zeros(98, bool)
+        for l in range(98):
+            h = hm[l].copy()
+            y, x = np.unravel_index(int(h.argmax()), h.shape)
+            v1 = h[y, x]
+            h[max(0, y - 2):y + 3, max(0, x - 2):x + 3] = -np.inf
+            t[l] = (v1 - h.max()) < 1e-3 * abs(v1)
+        tie.append(np.repeat(t, 2))
+    rxy, rsc, tie = np.array(rxy), np.array(rsc), np.array(tie)
     assert tie.mean() < 0.05
-    ref = np.where(tie, xy32, rxy)
-    dpx, dsc = np.abs(xy - ref).max() * 128, np.abs(sc - rsc).max()
-    print("teacher@128 cuda vs oracle: %.2e px, %.2e score (%d near-tied landmark coordinates vs the fp32 oracle)" % (dpx, dsc, int(tie.sum())))
+    dpx, dsc = (np.abs(xy - rxy) * ~tie).max() * 128, np.abs(sc - rsc).max()
+    print("teacher@128 cuda vs fp64 oracle: %.2e px, %.2e score (%d near-tied landmark coordinates left out)" % (dpx, dsc, int(tie.sum())))
     assert dpx < TOL_PX_TC and dsc < TOL_SCORE_TC
