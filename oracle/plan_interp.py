@@ -95,6 +95,12 @@ class PlanInterp:
                     Ho, Wo = y.shape[1], y.shape[2]
                     parts = [y[:, a:a + th, b:b + tw].sum(dim=(1, 2)) for a in range(0, Ho, th) for b in range(0, Wo, tw)]
                     wr(op.outs[1], torch.stack(parts, 1).reshape(N, len(parts), 1, -1))
+            elif t == P.OP_GAP_SSE:
+                x = rd(op.ins[0])                                                        # (N, H, W, C)
+                ws, bs = op.w_ref
+                parts = x.reshape(N, -1, 32, x.shape[-1]).sum(dim=2)                    # (N, tiles, C): 32-pixel tiles
+                wr(op.outs[0], parts.reshape(N, parts.shape[1], 1, -1))
+                wr(op.outs[1], _act((x * torch.from_numpy(ws)).sum(-1, keepdim=True) + float(bs[0]), op.act))
             elif t == P.OP_SE_FC:
                 w1, w2 = op.w_ref
                 Cr = op.ints[1]

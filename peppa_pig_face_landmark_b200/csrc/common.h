@@ -11,7 +11,7 @@ namespace skps {
 enum OpType {
     OP_CONV = 1, OP_DWCONV = 2, OP_MAXPOOL2 = 3, OP_RESIZE_NEAREST = 4, OP_UPSAMPLE_BILINEAR2X = 5,
     OP_COPY = 6, OP_GAP = 7, OP_AFFINE_ACT = 8, OP_SCSE = 9, OP_DET_DECODE = 10, OP_HM_DECODE = 11,
-    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14, OP_SE_FC = 15, OP_DWPW = 16, OP_STEM_BLOCK = 17
+    OP_SCALE_CH = 12, OP_UPCAT_DW = 13, OP_ADDN = 14, OP_SE_FC = 15, OP_DWPW = 16, OP_STEM_BLOCK = 17, OP_GAP_SSE = 18
 };
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_SILU = 3, ACT_SIGMOID = 4, ACT_HSIGMOID = 5 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_SPLIT16 = 2 };   // SPLIT16: fp16 hi plane + fp16 lo plane, v = hi + lo
@@ -228,6 +228,10 @@ int launch_se_fc(const TView& part, const TView& gate, const float* w1t, const f
                  int Cr, int act1, int act2, int hw, int batch, cudaStream_t s);
 // feat.base != null: hm holds the score maps only and the x/y offsets are w_off/b_off ([2P][K], [2P]) applied to feat at the arg-max pixel
 // part != null: the head conv wrote per-tile (max, arg-max) rows instead of the map (FLAG_HM_PART); hm is then only its shape
+// scSE front end (ops_misc.cu): x (N,H,W,C) -> per-tile channel sums part (N,tiles,C) + the sSE map act(x . w + b) (N,H,W,1)
+constexpr int GAP_SSE_TILE = 32;     // pixels per tile (rows of `part` per sample = H*W / 32)
+int launch_gap_sse(const TView& x, const TView& part, const TView& sse, const float* w, float bias, int act, int batch,
+                   cudaStream_t s);
 int launch_hm_decode(const TView& hm, const TView& feat, const float* w_off, const float* b_off, const TView& xy,
                      const TView& score, int npts, int batch, cudaStream_t s, const TView* part = nullptr);
 

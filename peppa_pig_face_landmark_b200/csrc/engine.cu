@@ -182,6 +182,9 @@ static int run_ops(skps_engine* e, int batch, cudaStream_t s, int first = 0, int
             case OP_AFFINE_ACT: rc = launch_affine_act(in0, out0, w, b, op.act, batch, s); break;
             case OP_SCSE: rc = launch_scse(in0, in1, in2, out0, batch, s); break;
             case OP_SCALE_CH: rc = launch_scale_ch(in0, in1, out0, batch, s); break;
+            case OP_GAP_SSE:
+                rc = launch_gap_sse(in0, out0, out1, w, op.b_off >= 0 ? e->h_weights[op.b_off] : 0.f, op.act, batch, s);
+                break;
             case OP_SE_FC:
                 // in0 = per-tile channel sums [n][tiles][C]; w = W1^T [C][Cr], i[0] -> W2^T [Cr][C]; b = [b1 (Cr) | b2 (C)]
                 rc = launch_se_fc(in0, out0, w, b, e->d_weights + op.i[0], b + op.i[1], op.i[1], op.act, op.i[2], op.i[3],

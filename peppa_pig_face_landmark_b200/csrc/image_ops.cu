@@ -5,6 +5,7 @@
 // -fmad=false so float32 expressions round exactly like the numpy expressions they restate.
 #include "../../include/skps_b200.h"
 #include "common.h"
+#include "mpipe_kernels.h"
 
 namespace skps {
 
@@ -43,11 +44,9 @@ __device__ __forceinline__ int vblend(int h0, int h1, int b0, int b1) {
 // Letterbox (face_detector.py:45-71): BGR->RGB, resize to (rw,rh), pad 114.  One thread per
 // output pixel (3 channels); output is uint8 RGB NHWC, /255 happens in the first conv.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) letterbox_kernel(const uint8_t* __restrict__ frame, int H, int W, int pitch,
-                                                        uint8_t* __restrict__ out, int in_h, int in_w,
-                                                        int rw, int rh, int top, int left) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
+__device__ __forceinline__ void letterbox_px(const uint8_t* __restrict__ frame, int H, int W, int pitch,
+                                             uint8_t* __restrict__ out, int in_h, int in_w, int rw, int rh, int top, int left,
+                                             int x, int y) {
     if (x >= in_w) return;
     uint8_t* o = out + ((long long)y * in_w + x) * 3;
     int dx = x - left, dy = y - top;
@@ -65,6 +64,17 @@ __global__ void __launch_bounds__(256) letterbox_kernel(const uint8_t* __restric
         int h1 = r1[tx.i0 * 3 + c] * tx.w0 + r1[tx.i1 * 3 + c] * tx.w1;
         o[2 - c] = (uint8_t)vblend(h0, h1, ty.w0, ty.w1);      // BGR -> RGB
     }
+}
+__global__ void __launch_bounds__(256) letterbox_kernel(const uint8_t* __restrict__ frame, int H, int W, int pitch,
+                                                        uint8_t* __restrict__ out, int in_h, int in_w,
+                                                        int rw, int rh, int top, int left) {
+    letterbox_px(frame, H, W, pitch, out, in_h, in_w, rw, rh, top, left, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
+}
+__global__ void __launch_bounds__(256) mp_letterbox_kernel(const MpStreamDesc* __restrict__ d, uint8_t* __restrict__ out,
+                                                           size_t out_stride, int in_h, int in_w) {
+    const MpStreamDesc D = d[blockIdx.z];
+    letterbox_px(D.cur, D.H, D.W, D.W * 3, out + out_stride * blockIdx.z, in_h, in_w, D.rw, D.rh, D.top, D.left,
+                 blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -95,13 +105,10 @@ __device__ __forceinline__ CropGeo crop_geometry(const float* b, int H, int W, f
     return g;
 }
 
-__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, int pitch,
-                                                          const float* __restrict__ boxes, const int* __restrict__ count,
-                                                          float face_scale, float min_face,
-                                                          uint8_t* __restrict__ crops, int S, int* __restrict__ detail) {
-    const int face = blockIdx.z;
-    const int y = blockIdx.y;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void crop_px(const uint8_t* __restrict__ frame, int H, int W, int pitch,
+                                        const float* __restrict__ boxes, const int* __restrict__ count, float face_scale,
+                                        float min_face, uint8_t* __restrict__ crops, int S, int* __restrict__ detail,
+                                        int face, int x, int y) {
     if (x >= S) return;
     uint8_t* o = crops + (((long long)face * S + y) * S + x) * 3;
     const int n = *count;
@@ -133,6 +140,21 @@ __global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restr
         int h1 = p10 * tx.w0 + p11 * tx.w1;
         o[c] = (uint8_t)vblend(h0, h1, ty.w0, ty.w1);          // stays BGR (face_landmark.py:44)
     }
+}
+__global__ void __launch_bounds__(256) crop_resize_kernel(const uint8_t* __restrict__ frame, int H, int W, int pitch,
+                                                          const float* __restrict__ boxes, const int* __restrict__ count,
+                                                          float face_scale, float min_face,
+                                                          uint8_t* __restrict__ crops, int S, int* __restrict__ detail) {
+    crop_px(frame, H, W, pitch, boxes, count, face_scale, min_face, crops, S, detail, blockIdx.z, blockIdx.x * blockDim.x + threadIdx.x,
+            blockIdx.y);
+}
+__global__ void __launch_bounds__(256) mp_crop_kernel(const MpStreamDesc* __restrict__ d, const float* __restrict__ boxes,
+                                                      const int* __restrict__ count, int K, float face_scale, float min_face,
+                                                      uint8_t* __restrict__ crops, int S, int* __restrict__ detail) {
+    const int st = blockIdx.z / K, face = blockIdx.z - st * K;
+    const MpStreamDesc D = d[st];
+    crop_px(D.cur, D.H, D.W, D.W * 3, boxes + (size_t)4 * K * st, count + st, face_scale, min_face,
+            crops + (size_t)S * S * 3 * K * st, S, detail + (size_t)5 * K * st, face, blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -200,7 +222,7 @@ __device__ __forceinline__ float iou_nms(const float4 a, const float4 b) {
     return inter / (area + other - inter);
 }
 
-__global__ void __launch_bounds__(1024) detect_post_kernel(const float* __restrict__ raw, int rows,
+__device__ __forceinline__ void detect_post_body(const float* __restrict__ raw, int rows,
                                                            float score_thres, float iou_thres,
                                                            float scale, float pad_x, float pad_y,
                                                            float* __restrict__ kept_rows, int* __restrict__ kept_idx,
@@ -280,6 +302,21 @@ __global__ void __launch_bounds__(1024) detect_post_kernel(const float* __restri
         kept_rows[k * 16 + c] = v;
         if (c == 0) kept_idx[k] = row;
     }
+}
+__global__ void __launch_bounds__(1024) detect_post_kernel(const float* __restrict__ raw, int rows, float score_thres,
+                                                           float iou_thres, float scale, float pad_x, float pad_y,
+                                                           float* __restrict__ kept_rows, int* __restrict__ kept_idx,
+                                                           int* __restrict__ count, int max_det) {
+    detect_post_body(raw, rows, score_thres, iou_thres, scale, pad_x, pad_y, kept_rows, kept_idx, count, max_det);
+}
+__global__ void __launch_bounds__(1024) mp_detect_post_kernel(const MpStreamDesc* __restrict__ d, const float* __restrict__ raw,
+                                                              int rows, float score_thres, float iou_thres,
+                                                              float* __restrict__ kept_rows, int* __restrict__ kept_idx,
+                                                              int* __restrict__ count, int max_det) {
+    const int st = blockIdx.x;
+    const MpStreamDesc D = d[st];
+    detect_post_body(raw + (size_t)rows * 16 * st, rows, score_thres, iou_thres, D.scale, (float)D.left, (float)D.top,
+                     kept_rows + (size_t)16 * max_det * st, kept_idx + (size_t)max_det * st, count + st, max_det);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -422,6 +459,90 @@ __global__ void __launch_bounds__(256) absdiff_sum_kernel(const uint8_t* __restr
         for (int w = 0; w < 8; ++w) t += warp_sum[w];
         atomicAdd(sum, t);
     }
+}
+
+__global__ void mp_landmark_post_kernel(const float* __restrict__ xy, const int* __restrict__ detail, const int* __restrict__ count,
+                                        int K, int P, float* __restrict__ kps, int n) {
+    // per stream exactly landmark_post_kernel: element i of stream st
+    const int per = K * P;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= per * n) return;
+    const int st = g / per, i = g - st * per, f = i / P;
+    const float* x = xy + (size_t)2 * per * st;
+    const int* dt = detail + (size_t)5 * K * st;
+    float ox = 0.f, oy = 0.f;
+    if (f < count[st]) {
+        const int* d = dt + f * 5;          // [h, w, y1, x1, add]
+        float px = x[i * 2] * (float)d[1];
+        float py = x[i * 2 + 1] * (float)d[0];
+        ox = (float)((double)px + (double)d[3] - (double)d[4]);
+        oy = (float)((double)py + (double)d[2] - (double)d[4]);
+    }
+    kps[(size_t)2 * per * st + i * 2] = ox;
+    kps[(size_t)2 * per * st + i * 2 + 1] = oy;
+}
+
+__global__ void __launch_bounds__(256) mp_absdiff_kernel(const MpStreamDesc* __restrict__ d, unsigned long long* __restrict__ sum) {
+    // per stream exactly absdiff_sum_kernel (integer sums: the order of the atomic adds does not matter)
+    const MpStreamDesc D = d[blockIdx.y];
+    if (!D.have_prev) return;
+    const uint8_t* a = D.prev;
+    const uint8_t* b = D.cur;
+    const size_t n = (size_t)D.H * D.W * 3, nv = n / 16;
+    unsigned long long local = 0;
+    const uint4* a4 = reinterpret_cast<const uint4*>(a);
+    const uint4* b4 = reinterpret_cast<const uint4*>(b);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 x = a4[i], y = b4[i];
+        local += __vsadu4(x.x, y.x) + __vsadu4(x.y, y.y) + __vsadu4(x.z, y.z) + __vsadu4(x.w, y.w);
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = nv * 16 + threadIdx.x; i < n; i += blockDim.x) {
+            int dd = (int)a[i] - (int)b[i];
+            local += (unsigned)(dd < 0 ? -dd : dd);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    __shared__ unsigned long long warp_sum[8];
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += warp_sum[w];
+        atomicAdd(sum + blockIdx.y, t);
+    }
+}
+
+int launch_mp_absdiff(const MpStreamDesc* d, unsigned long long* diff, int n, size_t max_bytes, cudaStream_t s) {
+    size_t blocks = (max_bytes / 16 + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    if (blocks < 1) blocks = 1;
+    mp_absdiff_kernel<<<dim3((unsigned)blocks, n), 256, 0, s>>>(d, diff);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_mp_letterbox(const MpStreamDesc* d, uint8_t* out, size_t out_stride, int in_h, int in_w, int n, cudaStream_t s) {
+    mp_letterbox_kernel<<<dim3((in_w + 255) / 256, in_h, n), 256, 0, s>>>(d, out, out_stride, in_h, in_w);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_mp_detect_post(const MpStreamDesc* d, const float* raw, int rows, float score_thres, float iou_thres, float* kept_rows,
+                          int* kept_idx, int* count, int max_det, int n, cudaStream_t s) {
+    mp_detect_post_kernel<<<n, 1024, 0, s>>>(d, raw, rows, score_thres, iou_thres, kept_rows, kept_idx, count, max_det);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_mp_crop(const MpStreamDesc* d, const float* boxes, const int* count, int K, float face_scale, float min_face,
+                   uint8_t* crops, int S, int* detail, int n, cudaStream_t s) {
+    mp_crop_kernel<<<dim3((S + 255) / 256, S, K * n), 256, 0, s>>>(d, boxes, count, K, face_scale, min_face, crops, S, detail);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_mp_landmark_post(const float* xy, const int* detail, const int* count, int K, int P, float* kps, int n, cudaStream_t s) {
+    const int total = K * P * n;
+    mp_landmark_post_kernel<<<(total + 255) / 256, 256, 0, s>>>(xy, detail, count, K, P, kps, n);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int launch_mp_select(const float* det_rows, const int* det_count, int max_det, const int* flag, const float* track,

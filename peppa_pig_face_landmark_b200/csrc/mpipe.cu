@@ -36,6 +36,7 @@ struct skps_mpipe {
     struct Slot {
         uint8_t* h_stage = nullptr;           // pinned staging for pageable frames [S][frame_bytes]
         int32_t* h_hw = nullptr; int32_t* h_have_prev = nullptr; int32_t* h_geom = nullptr;     // pinned, uploaded per batch
+        MpStreamDesc* h_desc = nullptr;       // pinned: per-stream frame pointers + letterbox geometry of this batch
         int32_t* h_count = nullptr; int32_t* h_flag = nullptr; int32_t* h_det_count = nullptr;
         double* h_box = nullptr; double* h_kps = nullptr; float* h_scores = nullptr;
         cudaEvent_t ev_in = nullptr, ev_done = nullptr;
@@ -46,6 +47,7 @@ struct skps_mpipe {
     int32_t *d_hw = nullptr, *d_have_prev = nullptr, *d_flag = nullptr, *d_det_count = nullptr, *d_det_idx = nullptr;
     int32_t *d_count = nullptr, *d_detail = nullptr;
     unsigned long long* d_diff = nullptr;
+    MpStreamDesc* d_desc = nullptr;           // this batch's descriptors (uploaded on the compute stream, in order)
     float *d_det_rows = nullptr, *d_boxes = nullptr, *d_kps_now = nullptr;
     // temporal state
     double *d_prev_lm = nullptr, *d_prev_dx = nullptr, *d_track = nullptr, *d_out_kps = nullptr;
@@ -69,13 +71,13 @@ extern "C" SKPS_API void skps_mpipe_destroy(skps_mpipe* p) {
     if (p->s_copy) cudaStreamSynchronize(p->s_copy);
     for (uint8_t* f : p->d_frame) if (f) cudaFree(f);
     for (auto& sl : p->slot) {
-        void* host[] = {sl.h_stage, sl.h_hw, sl.h_have_prev, sl.h_geom, sl.h_count, sl.h_flag, sl.h_det_count, sl.h_box,
+        void* host[] = {sl.h_desc, sl.h_stage, sl.h_hw, sl.h_have_prev, sl.h_geom, sl.h_count, sl.h_flag, sl.h_det_count, sl.h_box,
                         sl.h_kps, sl.h_scores};
         for (void* q : host) if (q) cudaFreeHost(q);
         if (sl.ev_in) cudaEventDestroy(sl.ev_in);
         if (sl.ev_done) cudaEventDestroy(sl.ev_done);
     }
-    void* dev[] = {p->d_hw, p->d_have_prev, p->d_flag, p->d_det_count, p->d_det_idx, p->d_count, p->d_detail, p->d_diff,
+    void* dev[] = {p->d_desc, p->d_hw, p->d_have_prev, p->d_flag, p->d_det_count, p->d_det_idx, p->d_count, p->d_detail, p->d_diff,
                    p->d_det_rows, p->d_boxes, p->d_kps_now, p->d_prev_lm, p->d_prev_dx, p->d_track, p->d_out_kps,
                    p->d_track_f32, p->d_n_prev, p->d_prev_f32, p->d_state_idx, p->d_n_track};
     for (void* q : dev) if (q) cudaFree(q);
@@ -135,13 +137,14 @@ extern "C" SKPS_API int skps_mpipe_create(skps_engine* det, skps_engine* kps, co
         MP_HOST(sl.h_stage, p->frame_bytes * S);
         MP_HOST(sl.h_hw, sizeof(int32_t) * 2 * S); MP_HOST(sl.h_have_prev, sizeof(int32_t) * S);
         MP_HOST(sl.h_geom, sizeof(int32_t) * 8 * S);
+        MP_HOST(sl.h_desc, sizeof(MpStreamDesc) * S);
         MP_HOST(sl.h_count, sizeof(int32_t) * S); MP_HOST(sl.h_flag, sizeof(int32_t) * S); MP_HOST(sl.h_det_count, sizeof(int32_t) * S);
         MP_HOST(sl.h_box, sizeof(double) * 4 * K * S); MP_HOST(sl.h_kps, sizeof(double) * 2 * P * K * S);
         MP_HOST(sl.h_scores, sizeof(float) * P * K * S);
         if (cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate"); return fail("event"); }
     }
-    MP_DEV(p->d_hw, 8 * S); MP_DEV(p->d_have_prev, 4 * S); MP_DEV(p->d_flag, 4 * S); MP_DEV(p->d_det_count, 4 * S);
+    MP_DEV(p->d_desc, sizeof(MpStreamDesc) * S); MP_DEV(p->d_hw, 8 * S); MP_DEV(p->d_have_prev, 4 * S); MP_DEV(p->d_flag, 4 * S); MP_DEV(p->d_det_count, 4 * S);
     MP_DEV(p->d_det_idx, 4 * (size_t)p->max_det * S); MP_DEV(p->d_count, 4 * S); MP_DEV(p->d_detail, 4 * 5 * (size_t)K * S);
     MP_DEV(p->d_diff, 8 * S); MP_DEV(p->d_det_rows, 4 * 16 * (size_t)p->max_det * S); MP_DEV(p->d_boxes, 4 * 4 * (size_t)K * S);
     MP_DEV(p->d_kps_now, 4 * 2 * (size_t)P * K * S);
@@ -202,47 +205,37 @@ extern "C" SKPS_API int skps_mpipe_submit(skps_mpipe* p, int slot_i, const uint8
     SKPS_CUDA(cudaMemsetAsync(p->d_diff, 0, 8 * n, sx));
     uint8_t* det_in = (uint8_t*)skps_engine_input_ptr(p->det);
     const size_t det_in_bytes = (size_t)p->det_h * p->det_w * 3;
+    // per-stream frame pointers + letterbox geometry: one small upload, then every pre/post-processing step is ONE launch for
+    // all streams (it was 5 launches per stream and call - ~80 launch gaps of a 5 ms call at 16 streams)
+    size_t max_bytes = 0;
     for (int s = 0; s < n; ++s) {
         const int H = hw[2 * s], W = hw[2 * s + 1];
-        const int pos = (p->ring_pos[s] + 1) % 3;
-        const uint8_t* cur = p->d_frame[(size_t)s * 3 + pos];
-        if (sl.h_have_prev[s]) {
-            const uint8_t* prev = p->d_frame[(size_t)s * 3 + p->ring_pos[s]];
-            if (skps_frame_absdiff_sum(prev, cur, (size_t)H * W * 3, p->d_diff + s, sx)) return 1;
-        }
-        float scale; int rw, rh, top, left;
-        letterbox_geometry(H, W, p->det_h, p->det_w, &scale, &rw, &rh, &top, &left);
-        if (skps_letterbox(cur, H, W, W * 3, det_in + det_in_bytes * s, p->det_h, p->det_w, rw, rh, top, left, sx)) return 1;
-        memcpy(&sl.h_geom[8 * s], &scale, 4); sl.h_geom[8 * s + 1] = top; sl.h_geom[8 * s + 2] = left;
+        MpStreamDesc& D = sl.h_desc[s];
+        D.cur = p->d_frame[(size_t)s * 3 + (p->ring_pos[s] + 1) % 3];
+        D.prev = sl.h_have_prev[s] ? p->d_frame[(size_t)s * 3 + p->ring_pos[s]] : nullptr;
+        D.H = H; D.W = W; D.have_prev = sl.h_have_prev[s];
+        letterbox_geometry(H, W, p->det_h, p->det_w, &D.scale, &D.rw, &D.rh, &D.top, &D.left);
+        memcpy(&sl.h_geom[8 * s], &D.scale, 4); sl.h_geom[8 * s + 1] = D.top; sl.h_geom[8 * s + 2] = D.left;
+        if ((size_t)H * W * 3 > max_bytes) max_bytes = (size_t)H * W * 3;
     }
+    SKPS_CUDA(cudaMemcpyAsync(p->d_desc, sl.h_desc, sizeof(MpStreamDesc) * n, cudaMemcpyHostToDevice, sx));
+    if (launch_mp_absdiff(p->d_desc, p->d_diff, n, max_bytes, sx)) return 1;
+    if (launch_mp_letterbox(p->d_desc, det_in, det_in_bytes, p->det_h, p->det_w, n, sx)) return 1;
     if (launch_mp_decide(p->d_diff, p->d_hw, p->d_have_prev, p->d_flag, n, sx)) return 1;
     // the detector runs for every stream of the batch (one launch sequence); the gate only chooses whose rows are used
     if (skps_engine_forward(p->det, det_in, n, nullptr, sx)) return 1;
     const float* det_out = skps_engine_output_ptr(p->det, 0);
-    for (int s = 0; s < n; ++s) {
-        float scale; memcpy(&scale, &sl.h_geom[8 * s], 4);
-        if (skps_detect_post(det_out + (size_t)p->det_rows * 16 * s, p->det_rows, c.score_thres, c.iou_thres, scale,
-                             (float)sl.h_geom[8 * s + 2], (float)sl.h_geom[8 * s + 1], p->d_det_rows + (size_t)16 * p->max_det * s,
-                             p->d_det_idx + (size_t)p->max_det * s, p->d_det_count + s, p->max_det, sx))
-            return 1;
-    }
+    if (launch_mp_detect_post(p->d_desc, det_out, p->det_rows, c.score_thres, c.iou_thres, p->d_det_rows, p->d_det_idx,
+                              p->d_det_count, p->max_det, n, sx))
+        return 1;
     if (launch_mp_select(p->d_det_rows, p->d_det_count, p->max_det, p->d_flag, p->d_track_f32, p->d_n_track, c.track_iou,
                          c.alpha, (float)(1.0 - (double)c.alpha), c.min_face, K, p->d_boxes, p->d_count, n, sx))
         return 1;
     uint8_t* kps_in = (uint8_t*)skps_engine_input_ptr(p->kps);
-    const size_t crop_bytes = (size_t)p->kps_hw * p->kps_hw * 3;
-    for (int s = 0; s < n; ++s) {
-        const int H = hw[2 * s], W = hw[2 * s + 1];
-        const uint8_t* cur = p->d_frame[(size_t)s * 3 + (p->ring_pos[s] + 1) % 3];
-        if (skps_crop_resize(cur, H, W, W * 3, p->d_boxes + (size_t)4 * K * s, p->d_count + s, K, c.face_scale, c.kps_min_face,
-                             kps_in + crop_bytes * K * s, p->kps_hw, p->d_detail + (size_t)5 * K * s, sx))
-            return 1;
-    }
+    if (launch_mp_crop(p->d_desc, p->d_boxes, p->d_count, K, c.face_scale, c.kps_min_face, kps_in, p->kps_hw, p->d_detail, n, sx))
+        return 1;
     if (skps_engine_forward(p->kps, kps_in, n * K, nullptr, sx)) return 1;
-    for (int s = 0; s < n; ++s)
-        if (skps_landmark_post(skps_engine_output_ptr(p->kps, 0) + (size_t)2 * P * K * s, p->d_detail + (size_t)5 * K * s,
-                               p->d_count + s, K, P, p->d_kps_now + (size_t)2 * P * K * s, sx))
-            return 1;
+    if (launch_mp_landmark_post(skps_engine_output_ptr(p->kps, 0), p->d_detail, p->d_count, K, P, p->d_kps_now, n, sx)) return 1;
     MpTemporalArgs a;
     a.top_k = K; a.n_points = P;
     a.kps_now = p->d_kps_now; a.count = p->d_count; a.flag = p->d_flag; a.hw = p->d_hw; a.boxes4 = p->d_boxes;

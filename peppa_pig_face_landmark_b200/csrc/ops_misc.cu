@@ -822,6 +822,75 @@ int launch_gap(const TView& in, const TView& out, int batch, cudaStream_t s) {
 // One CTA = 8 samples (they share every weight load); weights are stored transposed ([C][Cr] and [Cr][C]) so the
 // threads of a warp read consecutive floats.  Fixed summation order.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// scSE front end (model.py:117-130): ONE pass over x (N,H,W,256) produces the per-tile channel sums the cSE branch needs
+// (mean -> FC -> ReLU -> FC -> sigmoid runs in se_fc_kernel) and the sSE map sigmoid(x . w + b).  Before: GlobalAveragePool
+// (53 us) + a 256->1 tensor-core conv (50 us) + two FC launches, each re-reading x or waiting on the other.
+// CTA = 32 pixels x 256 channels: thread = (4-channel group, 8-pixel group).
+// ------------------------------------------------------------------------------------------
+struct GapSseK {
+    const void* x; int x_fmt; long long x_plane; int x_ld, x_coff;
+    float* part; int part_ld, part_coff; int tiles;       // [n][tiles][part_ld]
+    float* sse; int sse_ld, sse_coff;                     // [n][H*W][sse_ld]
+    const float* w; float bias; int act; int HW;
+};
+
+__global__ void __launch_bounds__(256) gap_sse_kernel(const GapSseK p) {
+    __shared__ float4 s_sum[4][64];
+    __shared__ float s_dot[2][GAP_SSE_TILE];
+    const int tid = threadIdx.x, cq = tid & 63, pg = tid >> 6;
+    const int tile = blockIdx.x, n = blockIdx.y;
+    const float4 w4 = *reinterpret_cast<const float4*>(p.w + 4 * cq);
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dot[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long pix = (long long)n * p.HW + tile * GAP_SSE_TILE + pg * 8 + i;
+        const float4 v = ld4(p.x, p.x_fmt, p.x_plane, pix * p.x_ld + p.x_coff + 4 * cq);
+        csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+        dot[i] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, v.w * w4.w)));
+    }
+    // per-pixel dot products: reduce over the 64 channel groups (two warps per pixel group)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) dot[i] += __shfl_xor_sync(0xffffffffu, dot[i], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_dot[(tid >> 5) & 1][pg * 8 + i] = dot[i];
+    }
+    s_sum[pg][cq] = csum;
+    __syncthreads();
+    if (tid < GAP_SSE_TILE) {
+        const long long pix = (long long)n * p.HW + tile * GAP_SSE_TILE + tid;
+        p.sse[pix * p.sse_ld + p.sse_coff] = apply_act(s_dot[0][tid] + s_dot[1][tid] + p.bias, p.act);
+    }
+    if (tid < 64) {
+        float4 t = s_sum[0][tid];
+#pragma unroll
+        for (int g = 1; g < 4; ++g) { const float4 u = s_sum[g][tid]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+        *reinterpret_cast<float4*>(p.part + ((long long)n * p.tiles + tile) * p.part_ld + p.part_coff + 4 * tid) = t;
+    }
+}
+
+int launch_gap_sse(const TView& x, const TView& part, const TView& sse, const float* w, float bias, int act, int batch,
+                   cudaStream_t s) {
+    SKPS_CHECK(x.base && part.base && sse.base && w, "gap_sse: null view");
+    SKPS_CHECK(x.C == 256 && x.c_stride == 1 && !((x.ld | x.c_off) & 3) && (x.H * x.W) % GAP_SSE_TILE == 0, "gap_sse: input view");
+    SKPS_CHECK(part.fmt == DT_F32 && part.c_stride == 1 && part.C == 256 && !((part.ld | part.c_off) & 3) &&
+               part.H * part.W == x.H * x.W / GAP_SSE_TILE, "gap_sse: partial-sum view");
+    SKPS_CHECK(sse.fmt == DT_F32 && sse.C == 1 && sse.H == x.H && sse.W == x.W, "gap_sse: sSE view");
+    GapSseK k;
+    k.x = x.base; k.x_fmt = x.fmt; k.x_plane = x.plane; k.x_ld = x.ld; k.x_coff = x.c_off;
+    k.part = (float*)part.base; k.part_ld = part.ld; k.part_coff = part.c_off; k.tiles = part.H * part.W;
+    k.sse = (float*)sse.base; k.sse_ld = sse.ld; k.sse_coff = sse.c_off;
+    k.w = w; k.bias = bias; k.act = act; k.HW = x.H * x.W;
+    gap_sse_kernel<<<dim3(k.tiles, batch), 256, 0, s>>>(k);
+    SKPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
 constexpr int SE_SAMPLES = 4;
 constexpr int SE_THREADS = 1024;
 struct SeFcK {

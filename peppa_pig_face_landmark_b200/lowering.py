@@ -1056,6 +1056,68 @@ def _fuse_hm_partial(pl):
         dec.flags |= P.FLAG_HM_PART
 
 
+def _fuse_gap_sse(pl):
+    """scSE attention (model.py:117-130; DecoderBlock attention2): cSE = sigmoid(FC(relu(FC(mean(x))))) and sSE = sigmoid(conv1x1(x))
+    both start with a full pass over x.  One kernel (OP_GAP_SSE) reads x once and writes per-tile channel sums and the sSE map;
+    the cSE MLP becomes the squeeze-excite FC kernel on those sums (OP_SE_FC).  Replaces GlobalAveragePool + 3 convs."""
+    if os.environ.get("SKPS_GAP_SSE", "1") == "0":
+        return
+
+    def same(a, b):
+        return a is not None and b is not None and a.buf is b.buf and (a.c_off, a.c_stride, a.C) == (b.c_off, b.c_stride, b.C)
+
+    def readers(v, skip=()):
+        return [o for o in pl.ops if o not in skip and any(same(i, v) for i in o.ins)]
+
+    for sc in list(pl.ops):
+        if sc.type != P.OP_SCSE:
+            continue
+        x, cse, sse = sc.ins[0], sc.ins[1], sc.ins[2]
+        fc2 = [o for o in pl.ops if o.type == P.OP_CONV and same(o.outs[0], cse)]
+        sconv = [o for o in pl.ops if o.type == P.OP_CONV and same(o.outs[0], sse)]
+        if len(fc2) != 1 or len(sconv) != 1:
+            continue
+        fc2, sconv = fc2[0], sconv[0]
+        fc1 = [o for o in pl.ops if o.type == P.OP_CONV and same(o.outs[0], fc2.ins[0])]
+        if len(fc1) != 1:
+            continue
+        fc1 = fc1[0]
+        gap = [o for o in pl.ops if o.type == P.OP_GAP and same(o.outs[0], fc1.ins[0])]
+        if len(gap) != 1 or not same(gap[0].ins[0], x) or not same(sconv.ins[0], x):
+            continue
+        gap = gap[0]
+        C, Cr, HW = x.C, fc1.outs[0].C, x.H * x.W
+        ok = (all(list(o.k) == [1, 1] and list(o.s) == [1, 1] and o.ins[1] is None and (len(o.ins) < 3 or o.ins[2] is None)
+                  for o in (fc1, fc2, sconv))
+              and not (fc1.flags & P.FLAG_TC) and not (fc2.flags & P.FLAG_TC) and sconv.outs[0].C == 1
+              and x.c_off == 0 and x.c_stride == 1 and x.C == x.buf.C and C == 256 and HW % 32 == 0
+              and fc2.outs[0].C == C and (C + Cr) * 8 * 4 <= 96 * 1024
+              and len(readers(gap.outs[0])) == 1 and len(readers(fc1.outs[0])) == 1
+              and len(readers(cse)) == 1 and len(readers(sse)) == 1)
+        if not ok:
+            continue
+        tiles = HW // 32
+        pb = pl.new_buf(C, tiles, 1, P.DT_F32, gap.name + ":tile_sums")
+        pv = P.View(pb, 0, 1, C)
+        ws = sconv.w_ref.reshape(-1)[:C].astype(np.float32)
+        bs = (sconv.b[:1] if sconv.b is not None else np.zeros(1, np.float32)).astype(np.float32)
+        sse.buf.dtype = P.DT_F32
+        g = P.Op(P.OP_GAP_SSE, [x], [pv, sse], sconv.act, w=ws, b=bs, name=gap.name + ":gap_sse")
+        g.w_ref = (ws, bs)
+        w1 = fc1.w_ref.reshape(Cr, C)
+        w2 = fc2.w_ref.reshape(C, Cr)
+        b1 = fc1.b if fc1.b is not None else np.zeros(Cr, np.float32)
+        b2 = fc2.b if fc2.b is not None else np.zeros(C, np.float32)
+        se = P.Op(P.OP_SE_FC, [pv], [fc2.outs[0]], fc1.act, w=np.ascontiguousarray(w1.T),
+                  b=np.concatenate([b1, b2]).astype(np.float32), ints=[0, Cr, fc2.act, HW], name=fc1.name + ":se_fc")
+        se.extra = np.ascontiguousarray(w2.T)
+        se.w_ref = (w1, w2)
+        i = min(pl.ops.index(o) for o in (gap, fc1, fc2, sconv))
+        for o in (gap, fc1, fc2, sconv):
+            pl.ops.remove(o)
+        pl.ops[i:i] = [g, se]
+
+
 def _fold_affine_into_producers(pl):
     """BatchNormalization (+ReLU) applied to a Concat of conv outputs (the ASPP tail, model.py Decoder/ASPP: conv1|conv2|conv3|
     pooled branch -> bn_act): a per-channel affine commutes with the channel concat, so it folds into every producing conv
@@ -1137,6 +1199,7 @@ def lower(onnx_path, in_hw, name=None, input_u8=True, use_tc=True):
         if input_u8:
             _fuse_stem_block(lw.plan)
         _fuse_hm_partial(lw.plan)
+        _fuse_gap_sse(lw.plan)
     chunk_env = os.environ.get("SKPS_L2_CHUNK_MB", "0")   # measured on B200: sub-batch sweeps are slower (15.8 vs 12.9 ms), off by default
     if chunk_env not in ("0", ""):
         lw.plan.plan_segments(l2_budget=int(chunk_env) << 20)

@@ -32,6 +32,8 @@ OP_ADDN = 14          # act(sum of up to 4 inputs), each optionally nearest-upsa
 OP_SE_FC = 15         # squeeze-excite gate: per-tile channel sums -> mean -> 1x1 -> act -> 1x1 -> act  (N,1,1,C)
 OP_DWPW = 16          # act(conv1x1(dw_act(depthwise3x3(x | concat(bilinear_x2(low), x))))): the depthwise output lives in smem only (csrc/conv_xf.cu)
 
+OP_GAP_SSE = 18       # scSE front end in one pass over x: per-tile channel sums (-> OP_SE_FC = cSE) and the sSE map act(x . w + b)
+
 OP_STEM_BLOCK = 17    # uint8 input -> stem 3x3 s2 -> dw3x3 -> 1x1 16->16 (+shortcut) -> 1x1 16->E -> dw3x3 s2, one kernel (csrc/stem_block.cu)
 
 OP_NAMES = {v: k for k, v in dict(globals()).items() if k.startswith("OP_")}

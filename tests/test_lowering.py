@@ -120,7 +120,9 @@ def test_student_plan_fusions():
     from peppa_pig_face_landmark_b200 import lowering, plan as P
     plan = lowering.lower(os.path.join(PRE, "kps_student.onnx"), (256, 256))
     kinds = [o.type for o in plan.ops]
-    assert kinds.count(P.OP_SE_FC) == 8 and kinds.count(P.OP_GAP) == 2
+    # 8 encoder squeeze-excite gates + the decoder's cSE branch (scSE front end fused: OP_GAP_SSE -> OP_SE_FC); the one
+    # GlobalAveragePool left is the ASPP pooling branch
+    assert kinds.count(P.OP_SE_FC) == 9 and kinds.count(P.OP_GAP) == 1 and kinds.count(P.OP_GAP_SSE) == 1
     assert kinds.count(P.OP_UPCAT_DW) == 0 and kinds.count(P.OP_SCALE_CH) == 0
     fused = [o for o in plan.ops if o.type == P.OP_DWPW]
     assert len(fused) == 6 and sum(1 for o in fused if o.ins[2] is not None) == 2          # 4 encoder pairs + 2 decoder heads
@@ -136,7 +138,7 @@ def test_student_plan_fusions():
     assert len(scaled) == 8 and all(o.ins[2] is not None and o.ins[0].buf.dtype == P.DT_SPLIT16 for o in scaled)
     for o in scaled:                     # each gate comes from the squeeze-excite op of the same block
         assert any(se.outs[0].buf is o.ins[2].buf for se in plan.ops if se.type == P.OP_SE_FC)
-    for se in (o for o in plan.ops if o.type == P.OP_SE_FC):
+    for se in (o for o in plan.ops if o.type == P.OP_SE_FC and not any(g.type == P.OP_GAP_SSE and g.outs[0].buf is o.ins[0].buf for g in plan.ops)):
         dw = [o for o in plan.ops if o.type == P.OP_DWCONV and len(o.outs) == 2 and o.outs[1].buf is se.ins[0].buf]
         assert len(dw) == 1 and dw[0].flags & P.FLAG_GAP_PARTIAL
         o = dw[0].outs[0]

