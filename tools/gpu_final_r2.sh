@@ -24,7 +24,7 @@ python tools/launch_table.py $OUT/det_b16_launches.csv 95 detector > $OUT/det_la
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/teacher_b64_launches.csv python tools/profile_student.py 64 1 teacher > $OUT/ncu_teacher.log 2>&1; echo "ncu teacher rc=$?" | tee -a $OUT/steps.log
 python tools/launch_table.py $OUT/teacher_b64_launches.csv 30 teacher > $OUT/teacher_launch_table.txt 2>&1; tail -1 $OUT/teacher_launch_table.txt
 echo "== ncu full: dominant conv, stem block, heat-map head" | tee -a $OUT/steps.log
-timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -o $OUT/full_final python tools/profile_op.py "#60,0,61" 256 1 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $OUT/steps.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -o $OUT/full_final python tools/profile_op.py "upsampler2/conv2/conv2.0/Conv" 256 1; timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -o $OUT/full_stem_hm python tools/profile_op.py "#0" 256 1 > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?" | tee -a $OUT/steps.log
 python tools/ncu_summary.py $OUT/full_final.ncu-rep > $OUT/full_final_summary.txt 2>&1
 grep -E "Kernel Name|time_duration|dram__bytes|lts__throughput|tensor_cycles" $OUT/full_final_summary.txt | cut -c1-130
 echo "== teacher sweep" | tee -a $OUT/steps.log
