@@ -16,6 +16,17 @@ plan.py.  Patterns handled:
   Resize nearest / linear x2, MaxPool 2x2 ceil, BatchNormalization [+Relu]          -> small ops
   yolov5-face Detect tail (face_detector graph nodes 502-820)                       -> OP_DET_DECODE
   heat-map arg-max tail (kps graph nodes 201-410; model.py:511-554)                 -> OP_HM_DECODE
+
+Post passes over the plan (each one a function below, each switchable by an environment variable for A/B runs):
+  _fuse_upsample_concat_dw   Resize(linear x2) -> Concat -> depthwise 3x3            -> OP_UPCAT_DW (no up-sampled tensor)
+  _fold_affine_into_producers BatchNorm(+ReLU) over a Concat of conv outputs (ASPP)  -> folded into the producing convs
+  _fuse_se_chain             depthwise -> GAP -> FC -> FC (squeeze-excite)           -> per-tile sums in the depthwise + OP_SE_FC
+  _fuse_dw_pw                depthwise 3x3 / OP_UPCAT_DW -> 1x1 conv                 -> OP_DWPW (csrc/conv_xf.cu)
+  _fuse_stem_block           stem 3x3 s2 -> dw+pw block -> 1x1 expand -> dw 3x3 s2    -> OP_STEM_BLOCK (csrc/stem_block.cu)
+  _fuse_hm_partial           heat-map head conv -> arg-max                           -> per-tile (max, arg-max) rows, map not stored
+  _fuse_gap_sse              scSE: GAP + FC + FC and the 1-channel sSE conv          -> OP_GAP_SSE + OP_SE_FC
+Kernel selection for a dense conv happens in the engine (csrc/engine.cu): transposed tcgen05 kernel (conv_tct.cu) when
+Cout fills the 128 TMEM lanes, transposed arg-max head (conv_hm.cu), pixels-on-lanes kernel (conv_tc.cu) otherwise.
 """
 import os
 
