@@ -1,4 +1,4 @@
-// The full-resolution head of the landmark encoder as ONE kernel (sm_100a, CUDA cores, float32):
+// The full-resolution head of the landmark encoder as ONE kernel (sm_100a; FP32 pipes + one tcgen05 K-step for the expansion):
 //
 //   uint8 crop (H x W x 3)  -> conv_stem 3x3 s2 (+/255, h-swish)                        16 ch @ H/2      [kps_student.onnx
 //                           -> blocks.0.0: depthwise 3x3 + ReLU -> 1x1 16->16 + shortcut 16 ch @ H/2       /student/encoder/
@@ -9,9 +9,11 @@
 // of 16- and 64-channel full-resolution tensors through HBM per 256-face batch (1.17 ms of a 7 ms step, r2 launch list);
 // fused, a CTA reads a 39 x 71 pixel window of the crop and writes an 8 x 16 tile of the E-channel quarter-resolution
 // tensor, everything in between lives in shared memory.  The work is ~1.2 M FMAs per tile on tensors with 3 / 16 input
-// channels - too thin for 128 x N x 16 tensor-core tiles - so it runs on the FP32 pipes with every dense weight taken from
-// the kernel-parameter (constant) bank: the unrolled inner loops issue FFMA with a constant operand and read each
-// activation from shared memory once per 16 outputs.
+// channels.  The stem, the block-0 depthwise and its 16->16 pointwise run on the FP32 pipes with every dense weight taken from
+// the kernel-parameter (constant) bank (FFMA with a constant operand, each activation read from shared memory once per 16
+// outputs); the 16->E expansion - half of the FMAs - is a single tcgen05 K-step per 128 window pixels (TC variant below,
+// the default; SKPS_STEM_TC=0 keeps it on the FP32 pipes).  Measured: 1.11 ms all-FP32 -> 1.01 ms with the expansion on
+// tensor cores -> 0.97 ms with the next tile's input window prefetched into registers (per 256-face batch).
 #include <cuda_fp16.h>
 #include <string.h>
 
