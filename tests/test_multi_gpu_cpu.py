@@ -75,3 +75,27 @@ def test_gloo_world2_pipeline_result_gather(tmp_path):
     assert d["frames"] == [0, 2, 4, 6] and d["shape"] == [4, 298]
     assert d["n"] == [0, 2] or d["n"] == [1, 2]          # rank 0's single face has box 0 / kps 0 / score 0: all-zero row
     assert d["box1"] == [11.0, 11.0, 11.0, 11.0]
+
+
+def test_bench_streams_frame_walk_is_cyclic_and_always_changes():
+    """tools/bench_streams.make_streams (the pipeline leg of bench.py): every stream walks the rank's `length` frames with its
+    own phase; consecutive frames of a stream always differ (so the frame-difference gate re-runs the detector on every
+    frame), also across the wrap-around, and ranks get different jitters."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import bench_streams
+    import frames
+
+    def maker(jitter=(0, 0)):                                  # a small stand-in for frames.frame_1080p
+        return frames.multi_face_frame(120, 160, (1, 1), 60, jitter)
+    for seed in (0, 1000, 2000):
+        seqs = bench_streams.make_streams(None, frames, maker, 5, length=4, seed0=seed, pin=False)
+        assert len(seqs) == 5 and all(len(s) == 4 for s in seqs)
+        for s in seqs:
+            for t in range(4):
+                assert (s[t] != s[(t + 1) % 4]).any()
+        assert seqs[1][0] is seqs[0][1] and seqs[4][3] is seqs[0][(3 + 4) % 4]       # phase-shifted views of the same frames
+    a = bench_streams.make_streams(None, frames, maker, 1, length=4, seed0=0, pin=False)
+    b = bench_streams.make_streams(None, frames, maker, 1, length=4, seed0=1000, pin=False)
+    assert any((x != y).any() for x, y in zip(a[0], b[0]))
