@@ -269,9 +269,13 @@ bool tct_applicable(const TcSetup& s) {
     if (!on) return false;
     const int stride = s.stride > 0 ? s.stride : 1;
     if (stride != 1 || s.kh != s.kw || s.kh < 3 || s.pad != s.dil * (s.kh - 1) / 2) return false;
-    if (s.W < 32 || s.W > TCT_N || TCT_N % s.W || s.H % (TCT_N / s.W)) return false;
+    // Cout threshold: below 96 the idle TMEM lanes cost more than the operand-bandwidth relief buys (measured with
+    // SKPS_TCT_MINC=64 on the ASPP 3x3 convs, Cout 64 on 16x16 maps: 73 vs 70 us on the pixels-on-lanes kernel)
+    static int min_c = -1;
+    if (min_c < 0) { const char* e = getenv("SKPS_TCT_MINC"); min_c = e ? atoi(e) : 96; }
+    if (s.W < 16 || s.W > TCT_N || TCT_N % s.W || s.H % (TCT_N / s.W)) return false;
     if (s.Cin < 64 || (s.Cin % 8) || (s.in_ld % 8) || (s.in_coff % 8)) return false;
-    if (s.Cout < 96 || s.Cout > TCT_M || (s.Cout % 8) || s.n_tiles != 1) return false;
+    if (s.Cout < min_c || s.Cout > TCT_M || (s.Cout % 8) || s.n_tiles != 1) return false;
     if (s.res || s.hm_val || s.out_fmt != DT_SPLIT16 || s.out_cstride != 1 || (s.out_ld % 8) || (s.out_coff % 8)) return false;
     return true;
 }
@@ -326,7 +330,8 @@ int tct_prepare(TctLayer& L, const TcSetup& s) {
     for (int plane = 0; plane < 2; ++plane) {
         cuuint64_t dims[4] = {(cuuint64_t)s.Cout, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.max_batch};
         cuuint64_t strides[3] = {(cuuint64_t)s.out_ld * 2, (cuuint64_t)s.W * s.out_ld * 2, (cuuint64_t)s.H * s.W * s.out_ld * 2};
-        cuuint32_t box[4] = {32, 32, 1, 1};
+        const cuuint32_t obw = (cuuint32_t)(s.W < 32 ? s.W : 32);                // 32 consecutive pixels = 32/obw whole rows
+        cuuint32_t box[4] = {32, obw, 32 / obw, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         char* base = (char*)s.out + (size_t)s.out_coff * 2 + (plane ? (size_t)s.out_plane * 2 : 0);
         CUresult r = enc(plane ? &L.o_lo : &L.o_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, estr,

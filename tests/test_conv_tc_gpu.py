@@ -84,6 +84,7 @@ def test_conv_tc_halo_row_mode(cfg, monkeypatch):
     (1, 32, 32, 64, 96, 3, 2, 0),        # dilated, 8-row tiles, Cout < 128 (the last lane quarter is clipped by the store)
     (3, 8, 128, 72, 104, 3, 1, 2),       # two-row tiles, K tail (72 channels), ragged Cout
     (2, 16, 256, 64, 128, 5, 1, 1),      # 5x5, one row per tile
+    (3, 16, 16, 160, 128, 3, 2, 1),      # 16-wide map: a tile is a whole image, store boxes of 2 rows x 16 pixels
 ])
 def test_conv_tct_transposed_kernel(cfg):
     err = _run(*cfg, out_split=True)
