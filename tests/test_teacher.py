@@ -143,6 +143,26 @@ def test_retargeted_128_exports_lower_and_match_oracle(tmp_path):
     assert np.abs(xy - rxy).max() * 128 < TOL_PX and np.abs(sc - rsc).max() < TOL_SCORE
 
 
+@pytest.mark.parametrize("size", [192, 320])
+def test_retargeted_odd_sizes_lower_and_match_oracle(tmp_path, size):
+    """Sizes the 128-pixel row-block tiling does not divide (48-/80-wide maps): the lowering still routes the dense convs to the
+    tensor-core kernels (ragged tiles) and the plan interpreter agrees with the oracle executor."""
+    import frames
+    from peppa_pig_face_landmark_b200 import graph_tools, lowering, plan as P
+    from oracle.plan_interp import PlanInterp
+    from oracle.onnx_exec import Session
+    from oracle.host_ref import resize_linear_u8
+    src = os.path.join(os.path.dirname(lowering.__file__), "pretrained", "kps_student.onnx")
+    path = graph_tools.retarget_input_size(src, str(tmp_path / "s.onnx"), size)
+    plan = lowering.lower(path, (size, size))
+    convs = [o for o in plan.ops if o.type == P.OP_CONV]
+    assert sum(1 for o in convs if o.flags & P.FLAG_TC) >= len(convs) - 6
+    crop = resize_linear_u8(frames.crop_variants(1)[0], size, size)[None]
+    xy, sc = PlanInterp(plan).run(crop)
+    o, k = Session(path).run(crop[0].transpose(2, 0, 1)[None].astype(np.float32) / np.float32(255))
+    assert np.abs(xy[0] - o.reshape(-1)).max() * size < 1e-3 and np.abs(sc[0] - k.reshape(-1)).max() < 1e-4
+
+
 @pytest.mark.gpu
 def test_student_128_cuda_matches_oracle(tmp_path):
     import frames
